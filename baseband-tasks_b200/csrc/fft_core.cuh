@@ -1,0 +1,272 @@
+// Shared-memory Stockham FFT building block for sm_100a.
+//
+// Replaces the np.fft.{fft,ifft} calls the reference's NumpyFFTMaker makes
+// (baseband_tasks/fourier/numpy.py:33-49).  One FFT of N = 2^LOG2N points is
+// computed by T = N/E cooperating threads, each holding E (<=16) complex
+// values in registers.  Every radix-R stage (R <= 16) is a register-resident
+// butterfly; between stages the values are exchanged through a padded,
+// bank-conflict-free shared-memory buffer.  Thread t owns elements
+// t + T*e (e < E) both before and after the transform, so global loads and
+// stores of consecutive threads are coalesced and no bit-reversal pass exists.
+//
+// The header is plain C++ so that the same code can be compiled by g++ in the
+// kernel-emulation test harness (tests/emu) as well as by nvcc.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BBT_HD __host__ __device__ __forceinline__
+#define BBT_D __device__ __forceinline__
+#else
+#define BBT_HD inline
+#define BBT_D inline
+#endif
+
+namespace bbt {
+
+struct alignas(8) cf {
+  float x, y;
+};
+struct alignas(16) cf2 {  // two adjacent series (e.g. both polarizations)
+  cf a, b;
+};
+
+BBT_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+BBT_HD cf operator+(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
+BBT_HD cf operator-(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+BBT_HD cf cmul(cf a, cf b) {
+  return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+BBT_HD cf cmulc(cf a, cf b) {  // a * conj(b)
+  return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+BBT_HD cf cconj(cf a) { return mk(a.x, -a.y); }
+BBT_HD cf cscale(cf a, float s) { return mk(a.x * s, a.y * s); }
+BBT_HD cf mul_mi(cf a) { return mk(a.y, -a.x); }  // a * (-i)
+BBT_HD cf mul_pi(cf a) { return mk(-a.y, a.x); }  // a * (+i)
+
+// ---------------------------------------------------------------------------
+// Register butterflies: forward DFT (exp(-2 pi i nk/R)), natural order in and
+// out, fully unrolled so everything stays in registers.
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<1> {
+  static BBT_HD void run(cf*) {}
+};
+
+template <>
+struct Dft<2> {
+  static BBT_HD void run(cf* v) {
+    cf a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  }
+};
+
+template <>
+struct Dft<4> {
+  static BBT_HD void run(cf* v) {
+    cf s02 = v[0] + v[2], d02 = v[0] - v[2];
+    cf s13 = v[1] + v[3], d13 = mul_mi(v[1] - v[3]);
+    v[0] = s02 + s13;
+    v[1] = d02 + d13;
+    v[2] = s02 - s13;
+    v[3] = d02 - d13;
+  }
+};
+
+// R = R1*R2 with n = R2*n1 + n2 and k = k1 + R1*k2:
+// X[k1 + R1 k2] = sum_n2 W_R^{n2 k1} W_R2^{n2 k2} sum_n1 x[R2 n1 + n2] W_R1^{n1 k1}
+template <>
+struct Dft<8> {
+  static BBT_HD void run(cf* v) {
+    const float h = 0.70710678118654752440f;
+    cf a[4] = {v[0], v[2], v[4], v[6]};
+    cf b[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4>::run(a);
+    Dft<4>::run(b);
+    // b[k1] *= W8^{k1}
+    b[1] = mk((b[1].x + b[1].y) * h, (b[1].y - b[1].x) * h);
+    b[2] = mul_mi(b[2]);
+    b[3] = mk((b[3].y - b[3].x) * h, -(b[3].x + b[3].y) * h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = a[k] + b[k];
+      v[k + 4] = a[k] - b[k];
+    }
+  }
+};
+
+template <>
+struct Dft<16> {
+  static BBT_HD void run(cf* v) {
+    // cos/sin of pi/8 multiples.
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    const float h = 0.70710678118654752440f;
+    cf a[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+#pragma unroll
+      for (int n1 = 0; n1 < 4; ++n1) a[n2][n1] = v[4 * n1 + n2];
+      Dft<4>::run(a[n2]);
+    }
+    // a[n2][k1] *= W16^{n2 k1}; W16^m = cos(m pi/8) - i sin(m pi/8).
+    a[1][1] = cmul(a[1][1], mk(c1, -s1));
+    a[1][2] = mk((a[1][2].x + a[1][2].y) * h, (a[1][2].y - a[1][2].x) * h);
+    a[1][3] = cmul(a[1][3], mk(s1, -c1));
+    a[2][1] = mk((a[2][1].x + a[2][1].y) * h, (a[2][1].y - a[2][1].x) * h);
+    a[2][2] = mul_mi(a[2][2]);
+    a[2][3] = mk((a[2][3].y - a[2][3].x) * h, -(a[2][3].x + a[2][3].y) * h);
+    a[3][1] = cmul(a[3][1], mk(s1, -c1));
+    a[3][2] = mk((a[3][2].y - a[3][2].x) * h, -(a[3][2].x + a[3][2].y) * h);
+    a[3][3] = cmul(a[3][3], mk(-c1, s1));  // W16^9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+      cf b[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
+      Dft<4>::run(b);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = b[k2];
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Configuration of a block FFT.
+constexpr int kLog2TwiddleTable = 13;  // largest single-pass FFT: 8192 points
+constexpr int kTwiddleTable = 1 << kLog2TwiddleTable;
+
+template <int LOG2N>
+struct FftCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2E = LOG2N < 4 ? LOG2N : 4;
+  static constexpr int E = 1 << LOG2E;  // elements per thread
+  static constexpr int T = N / E;       // threads per FFT
+  static constexpr int NPAD = N + (N >> 4);  // exchange slots per FFT
+  // CTA shape: 256 threads (512 for the 8192-point transform), G FFTs per CTA.
+  static constexpr int THREADS = T > 256 ? T : 256;
+  static constexpr int G = THREADS / T;
+  static constexpr size_t SMEM_BYTES = (size_t)G * NPAD * sizeof(float) * 2;
+};
+
+BBT_HD int padslot(int p) { return p + (p >> 4); }
+
+// Exchange-buffer addressing.  G FFTs ("lanes") share one CTA.
+//  LaneFast: consecutive threads work on consecutive lanes (column tiles);
+//  slot = padslot(p) * G + g.
+//  LaneSlow: consecutive threads work on consecutive elements of one FFT;
+//  slot = g * NPAD + padslot(p).
+struct SmemLaneFast {
+  cf* base;
+  int g, G;
+  BBT_HD cf& at(int p) const { return base[padslot(p) * G + g]; }
+};
+template <int NPAD>
+struct SmemLaneSlow {
+  cf* base;  // already offset to this lane
+  BBT_HD cf& at(int p) const { return base[padslot(p)]; }
+};
+
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+#define BBT_SYNC() __syncthreads()
+#define BBT_LDG(p) __ldg(p)
+#elif defined(BBT_EMULATE)
+}  // namespace bbt
+void bbt_emu_syncthreads();
+namespace bbt {
+#define BBT_SYNC() bbt_emu_syncthreads()
+#define BBT_LDG(p) (*(p))
+#else
+#define BBT_SYNC()
+#define BBT_LDG(p) (*(p))
+#endif
+
+BBT_HD cf ldtw(const cf* tw, int i) {
+#if defined(__CUDA_ARCH__)
+  float2 w = __ldg(reinterpret_cast<const float2*>(tw) + i);
+  return mk(w.x, w.y);
+#else
+  return tw[i];
+#endif
+}
+
+// One Stockham stage: Ns = 2^LOG2NS points already combined, radix 2^LOG2R.
+// tw is the table exp(-2 pi i m / kTwiddleTable), m < kTwiddleTable.
+template <int LOG2N, int LOG2NS, int LOG2R, class Smem>
+BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
+  using C = FftCfg<LOG2N>;
+  constexpr int R = 1 << LOG2R;
+  constexpr int Ns = 1 << LOG2NS;
+  constexpr int NB = C::E / R;  // butterflies per thread
+  constexpr bool last = (LOG2NS + LOG2R == LOG2N);
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + C::T * q;
+    const int k = j & (Ns - 1);
+    cf b[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) b[r] = v[q + r * NB];
+    if constexpr (LOG2NS > 0) {
+      // w^r, w = exp(-2 pi i k / (Ns R)); table index k * TABLE / (Ns R).
+      const int kk = k << (kLog2TwiddleTable - LOG2NS - LOG2R);
+      cf w[R];
+      w[1] = ldtw(tw, kk);
+      if constexpr (R > 2) w[2] = ldtw(tw, 2 * kk);
+      if constexpr (R > 4) w[4] = ldtw(tw, 4 * kk);
+      if constexpr (R > 8) w[8] = ldtw(tw, 8 * kk);
+      if constexpr (R > 2) w[3] = cmul(w[2], w[1]);
+      if constexpr (R > 4) {
+        w[5] = cmul(w[4], w[1]);
+        w[6] = cmul(w[4], w[2]);
+        w[7] = cmul(w[4], w[3]);
+      }
+      if constexpr (R > 8) {
+#pragma unroll
+        for (int r = 9; r < 16; ++r) w[r] = cmul(w[8], w[r - 8]);
+      }
+#pragma unroll
+      for (int r = 1; r < R; ++r) b[r] = cmul(b[r], w[r]);
+    }
+    Dft<R>::run(b);
+    if constexpr (last) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[q + r * NB] = b[r];
+    } else {
+      const int p0 = ((j - k) << LOG2R) + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) sm.at(p0 + r * Ns) = b[r];
+    }
+  }
+  if constexpr (!last) {
+    BBT_SYNC();
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) v[e] = sm.at(t + C::T * e);
+    BBT_SYNC();
+  }
+}
+
+template <int LOG2N, int LOG2NS, class Smem>
+struct FftStages {
+  static BBT_HD void run(cf* v, int t, const cf* __restrict__ tw,
+                         const Smem& sm) {
+    using C = FftCfg<LOG2N>;
+    constexpr int REM = LOG2N - LOG2NS;
+    constexpr int LR = REM < C::LOG2E ? REM : C::LOG2E;
+    fft_stage<LOG2N, LOG2NS, LR, Smem>(v, t, tw, sm);
+    FftStages<LOG2N, LOG2NS + LR, Smem>::run(v, t, tw, sm);
+  }
+};
+template <int LOG2N, class Smem>
+struct FftStages<LOG2N, LOG2N, Smem> {
+  static BBT_HD void run(cf*, int, const cf* __restrict__, const Smem&) {}
+};
+
+// Forward FFT of the N values spread over T threads (v[e] <-> t + T*e).
+// All threads of the CTA must call this together (it synchronises).
+template <int LOG2N, class Smem>
+BBT_HD void block_fft(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
+  FftStages<LOG2N, 0, Smem>::run(v, t, tw, sm);
+}
+
+}  // namespace bbt

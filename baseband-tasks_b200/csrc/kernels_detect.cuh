@@ -1,0 +1,290 @@
+// Detection and integration kernels.
+//   power / square      functions.py:15-16,132-143
+//   channelize+power(+integrate) fused   channelize.py:73-74 + functions.py:132-143
+//                                        + integration.py:273-303
+//   integrate           integration.py:290-303 (segmented sums + counts)
+//   fold                integration.py:380-395 (phase-bin scatter add)
+#pragma once
+#include "kernels_fft.cuh"
+
+namespace bbt {
+
+struct alignas(16) f4 {
+  float x, y, z, w;
+};
+
+BBT_HD f4 stokes_like(cf a, cf b) {
+  // [|X|^2, |Y|^2, Re(X conj Y), Im(X conj Y)]  (functions.py:138-142)
+  f4 r;
+  r.x = a.x * a.x + a.y * a.y;
+  r.y = b.x * b.x + b.y * b.y;
+  r.z = a.x * b.x + a.y * b.y;
+  r.w = a.y * b.x - a.x * b.y;
+  return r;
+}
+
+// (A, 2, B) complex -> (A, 4, B) float.
+BBT_GLOBAL void power_kernel(const cf* BBT_RESTRICT in, float* BBT_RESTRICT out,
+                             long long A, long long B) {
+  const long long total = A * B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long a = i / B, b = i % B;
+    const f4 p = stokes_like(in[(a * 2) * B + b], in[(a * 2 + 1) * B + b]);
+    float* o = out + (a * 4) * B + b;
+    o[0] = p.x;
+    o[B] = p.y;
+    o[2 * B] = p.z;
+    o[3 * B] = p.w;
+  }
+}
+
+BBT_GLOBAL void square_kernel(const float* BBT_RESTRICT in, float* BBT_RESTRICT out,
+                              long long n, int is_complex) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (is_complex) {
+      const float re = in[2 * i], im = in[2 * i + 1];
+      out[i] = re * re + im * im;
+    } else {
+      out[i] = in[i] * in[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused Channelize(n) -> Power (-> Integrate).
+// Input  x[(j*n + i)][m][p]  complex, j spectrum, i sample in block, m < M,
+//        p polarization (2).
+// Output (no integrate)  out[j][k][m][4] float.
+// Output (integrate)     sum[b][k][m][4] += ..., count[b] += width, for bins
+//        b with spectra [offsets[b], offsets[b+1]) clipped to the spectra
+//        [j_first, j_first + n_spec) present in this call.
+struct ChanPowArgs {
+  const cf2* in;
+  float* out;             // out or sum
+  unsigned long long* count;
+  const long long* offsets;  // bin edges in spectra (absolute)
+  const cf* tw;
+  long long M;
+  long long n_spec;       // spectra in this call
+  long long j_first;      // absolute index of the first spectrum in `in`
+  long long b_first;      // first bin handled (blockIdx.y = 0)
+  long long msub;         // concurrent spectrum sub-streams per bin
+};
+
+template <int LOG2N, bool LANEFAST, bool INTEGRATE>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
+  using C = FftCfg<LOG2N>;
+  cf* smem = BBT_SMEM(cf);
+  cf* smem1 = smem + (size_t)C::G * C::NPAD;
+  const int tid = threadIdx.x;
+  int t, g;
+  if (LANEFAST) {
+    g = tid % C::G;
+    t = tid / C::G;
+  } else {
+    t = tid % C::T;
+    g = tid / C::T;
+  }
+  const long long lane = (long long)blockIdx.x * C::G + g;
+  const long long m = lane % a.M, jsub = lane / a.M;
+  long long lo, hi;  // spectra (relative to j_first) this CTA walks through
+  long long b = 0;
+  if (INTEGRATE) {
+    b = a.b_first + blockIdx.y;
+    lo = a.offsets[b] - a.j_first;
+    hi = a.offsets[b + 1] - a.j_first;
+    if (lo < 0) lo = 0;
+    if (hi > a.n_spec) hi = a.n_spec;
+  } else {
+    lo = 0;
+    hi = a.n_spec;
+  }
+  const bool lane_ok = jsub < a.msub;
+  f4 acc[C::E];
+  if (INTEGRATE) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) acc[e].x = acc[e].y = acc[e].z = acc[e].w = 0.f;
+  }
+  for (long long j0 = lo; j0 < hi; j0 += a.msub) {
+    const long long j = j0 + jsub;
+    const bool valid = lane_ok && j < hi;
+    const cf2* src = a.in + (j * C::N) * a.M + m;
+    cf v0[C::E], v1[C::E];
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      if (valid) {
+        const cf2 x = src[(long long)(t + C::T * e) * a.M];
+        v0[e] = x.a;
+        v1[e] = x.b;
+      } else {
+        v0[e] = v1[e] = mk(0.f, 0.f);
+      }
+    }
+    if (LANEFAST) {
+      SmemLaneFast s0{smem, g, C::G}, s1{smem1, g, C::G};
+      block_fft<LOG2N>(v0, t, a.tw, s0);
+      block_fft<LOG2N>(v1, t, a.tw, s1);
+    } else {
+      SmemLaneSlow<C::NPAD> s0{smem + (size_t)g * C::NPAD},
+          s1{smem1 + (size_t)g * C::NPAD};
+      block_fft<LOG2N>(v0, t, a.tw, s0);
+      block_fft<LOG2N>(v1, t, a.tw, s1);
+    }
+    if (valid) {
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        const f4 p = stokes_like(v0[e], v1[e]);
+        if (INTEGRATE) {
+          acc[e].x += p.x;
+          acc[e].y += p.y;
+          acc[e].z += p.z;
+          acc[e].w += p.w;
+        } else {
+          f4* o = reinterpret_cast<f4*>(a.out) +
+                  ((j * C::N + (t + C::T * e)) * a.M + m);
+          *o = p;
+        }
+      }
+    }
+  }
+  if (INTEGRATE) {
+    if (lane_ok && hi > lo) {
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        float* o = a.out + (((b * C::N) + (t + C::T * e)) * a.M + m) * 4;
+        atomic_add(o + 0, acc[e].x);
+        atomic_add(o + 1, acc[e].y);
+        atomic_add(o + 2, acc[e].z);
+        atomic_add(o + 3, acc[e].w);
+      }
+    }
+    if (tid == 0 && blockIdx.x == 0 && hi > lo)
+      atomic_add(a.count + b, (unsigned long long)(hi - lo));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Integrate: sum[b][c] += sum_{i in [offsets[b], offsets[b+1])} in[i][c],
+// count[b] += width, with the bin clipped to the samples
+// [i_first, i_first + n) present in this call (integration.py:290-303).
+struct IntegrateArgs {
+  const float* in;
+  float* sum;
+  unsigned long long* count;
+  const long long* offsets;
+  long long inner, n, i_first, b_first, msub;
+};
+
+BBT_GLOBAL void integrate_kernel(IntegrateArgs a) {
+  const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long c = lane % a.inner, sub = lane / a.inner;
+  const long long b = a.b_first + blockIdx.y;
+  long long lo = a.offsets[b] - a.i_first, hi = a.offsets[b + 1] - a.i_first;
+  if (lo < 0) lo = 0;
+  if (hi > a.n) hi = a.n;
+  if (hi <= lo) return;
+  if (lane == 0) atomic_add(a.count + b, (unsigned long long)(hi - lo));
+  if (sub >= a.msub) return;
+  float acc = 0.f;
+  for (long long i = lo + sub; i < hi; i += a.msub) acc += a.in[i * a.inner + c];
+  atomic_add(a.sum + b * a.inner + c, acc);
+}
+
+// ---------------------------------------------------------------------------
+// Fold: for every sample i of time bin b, phase bin
+//   p = int(((phase(i) mod 1) * n_phase))        (integration.py:389-391)
+// and sum[b][p][c] += x[i][c], count[b][p] += 1  (integration.py:394-395).
+// phase(i) = Horner(coef, dt), dt = (i_abs - i_ref) / rate, all in float64
+// with individually rounded operations (no FMA), so that the bin assignment
+// is bit-identical to the oracle's numpy arithmetic.  Alternatively the phase
+// bins may be supplied precomputed (pbin != nullptr) for arbitrary callables.
+// With POWER the input is [n][M][2] complex and the four polarization
+// products are formed on the fly (Power -> Fold without an HBM round trip).
+struct FoldArgs {
+  const void* in;
+  float* sum;                 // [n_tbin][n_phase][inner]
+  unsigned long long* count;  // [n_tbin][n_phase]
+  const long long* lo;        // [n_tbin] first sample (absolute) of bin
+  const long long* hi;        // [n_tbin] one past last sample of bin
+  const int* pbin;            // optional precomputed phase bins [n]
+  long long inner;            // floats per sample in the output
+  long long n, i_first;       // samples in this call; absolute index of first
+  long long b_first;          // time bin of blockIdx.y = 0
+  long long i_ref;            // sample index at which dt = 0
+  double rate;
+  double coef[8];
+  int ncoef;
+  int n_phase;
+  int use_smem;               // privatise the profile in shared memory
+};
+
+BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
+  const double dt = ddiv((double)(i_abs - a.i_ref), a.rate);
+  double ph = a.coef[a.ncoef - 1];
+  for (int k = a.ncoef - 2; k >= 0; --k) ph = dadd(dmul(ph, dt), a.coef[k]);
+  double r = fmod(ph, 1.0);
+  if (r < 0.) r = dadd(r, 1.0);  // numpy's floored modulo
+  return (int)dmul(r, (double)a.n_phase);
+}
+
+template <bool POWER>
+BBT_GLOBAL void fold_kernel(FoldArgs a) {
+  float* hist = BBT_SMEM(float);
+  unsigned* hcnt = reinterpret_cast<unsigned*>(hist + (size_t)a.n_phase * a.inner);
+  const long long b = a.b_first + blockIdx.y;
+  long long lo = a.lo[b] - a.i_first, hi = a.hi[b] - a.i_first;
+  if (lo < 0) lo = 0;
+  if (hi > a.n) hi = a.n;
+  // This CTA's share of the bin.
+  const long long per = (hi - lo + gridDim.x - 1) / (long long)gridDim.x;
+  const long long i0 = lo + per * blockIdx.x;
+  const long long i1 = (i0 + per < hi) ? i0 + per : hi;
+  const int nh = a.n_phase * (int)a.inner;
+  if (a.use_smem) {
+    for (int q = threadIdx.x; q < nh; q += blockDim.x) hist[q] = 0.f;
+    for (int q = threadIdx.x; q < a.n_phase; q += blockDim.x) hcnt[q] = 0u;
+    BBT_SYNC();
+  }
+  float* gsum = a.sum + b * (long long)nh;
+  unsigned long long* gcnt = a.count + b * a.n_phase;
+  const long long width = POWER ? a.inner / 4 : a.inner;  // input items per sample
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    int p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
+    if (p < 0) p = 0;
+    if (p >= a.n_phase) p = a.n_phase - 1;
+    float* dsum = (a.use_smem ? hist : gsum) + (long long)p * a.inner;
+    if (POWER) {
+      const cf2* x = static_cast<const cf2*>(a.in) + i * width;
+      for (long long m = 0; m < width; ++m) {
+        const f4 q = stokes_like(x[m].a, x[m].b);
+        atomic_add(dsum + 4 * m + 0, q.x);
+        atomic_add(dsum + 4 * m + 1, q.y);
+        atomic_add(dsum + 4 * m + 2, q.z);
+        atomic_add(dsum + 4 * m + 3, q.w);
+      }
+    } else {
+      const float* x = static_cast<const float*>(a.in) + i * width;
+      for (long long c = 0; c < width; ++c) atomic_add(dsum + c, x[c]);
+    }
+    if (a.use_smem) {
+#if defined(BBT_EMULATE)
+      __atomic_fetch_add(hcnt + p, 1u, __ATOMIC_RELAXED);
+#else
+      atomicAdd(hcnt + p, 1u);
+#endif
+    } else {
+      atomic_add(gcnt + p, 1ull);
+    }
+  }
+  if (a.use_smem) {
+    BBT_SYNC();
+    for (int q = threadIdx.x; q < nh; q += blockDim.x)
+      if (hist[q] != 0.f) atomic_add(gsum + q, hist[q]);
+    for (int q = threadIdx.x; q < a.n_phase; q += blockDim.x)
+      if (hcnt[q]) atomic_add(gcnt + q, (unsigned long long)hcnt[q]);
+  }
+}
+
+}  // namespace bbt

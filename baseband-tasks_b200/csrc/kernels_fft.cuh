@@ -1,0 +1,207 @@
+// Batched strided FFT kernels (c2c, r2c, c2r) built on block_fft.
+//
+// Data are viewed as [outer][n][inner] (C order); the transform runs along the
+// middle axis.  This one shape covers every FFT call site on the hot path:
+//   Channelize          axis=1 of (spf, n)+sample_shape  (channelize.py:57-74)
+//   Disperse small-N    axis=0 of (N,)+sample_shape      (dispersion.py:105-108)
+//   FFTMaker plugin     any axis of any shape            (fourier/base.py:262-311)
+// A CTA transforms G "lanes" (one lane = one (outer, inner) pair) at once.
+//   LANEFAST: lanes are consecutive inner columns of one outer index, so a
+//             warp touches G*8 contiguous bytes per FFT row (inner > 1).
+//   !LANEFAST: lanes are consecutive outer indices (inner == 1); consecutive
+//             threads of a lane touch consecutive elements.
+#pragma once
+#include "fft_core.cuh"
+#include "rt.cuh"
+
+namespace bbt {
+
+struct FftArgs {
+  const void* in;
+  void* out;
+  const cf* tw;     // exp(-2 pi i m / kTwiddleTable)
+  long long outer;  // number of outer indices
+  long long inner;  // number of inner columns
+  int inverse;      // 0 forward, 1 backward
+  float scale;      // applied to the output
+};
+
+template <int LOG2N, bool LANEFAST>
+struct LaneMap {
+  using C = FftCfg<LOG2N>;
+  int t, g;
+  long long b, c;  // outer index, inner column
+  bool valid;
+  BBT_HD LaneMap(int t_, int g_) : t(t_), g(g_), b(0), c(0), valid(true) {}
+  BBT_HD LaneMap(int tid, long long blk, const FftArgs& a) {
+    if (LANEFAST) {
+      // Lanes enumerate (outer, inner) pairs with the inner column fastest.
+      g = tid % C::G;
+      t = tid / C::G;
+      const long long lane = blk * C::G + g;
+      b = lane / a.inner;
+      c = lane % a.inner;
+      valid = lane < a.outer * a.inner;
+    } else {
+      t = tid % C::T;
+      g = tid / C::T;
+      b = blk * C::G + g;
+      c = 0;
+      valid = b < a.outer;
+    }
+  }
+};
+
+template <int LOG2N, bool LANEFAST>
+BBT_HD void lane_fft(cf* v, const LaneMap<LOG2N, LANEFAST>& m, const cf* tw,
+                     cf* smem) {
+  using C = FftCfg<LOG2N>;
+  if (LANEFAST) {
+    SmemLaneFast sm{smem, m.g, C::G};
+    block_fft<LOG2N>(v, m.t, tw, sm);
+  } else {
+    SmemLaneSlow<C::NPAD> sm{smem + (size_t)m.g * C::NPAD};
+    block_fft<LOG2N>(v, m.t, tw, sm);
+  }
+}
+
+// Complex to complex.
+template <int LOG2N, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2c_kernel(FftArgs a) {
+  using C = FftCfg<LOG2N>;
+  cf* smem = BBT_SMEM(cf);
+  const long long blk = blockIdx.x;
+  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  const cf* in = static_cast<const cf*>(a.in);
+  cf* out = static_cast<cf*>(a.out);
+  const long long base = m.b * C::N * a.inner + m.c;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) {
+    cf x = mk(0.f, 0.f);
+    if (m.valid) x = in[base + (long long)(m.t + C::T * e) * a.inner];
+    v[e] = a.inverse ? cconj(x) : x;
+  }
+  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  if (m.valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      cf y = cscale(v[e], a.scale);
+      out[base + (long long)(m.t + C::T * e) * a.inner] =
+          a.inverse ? cconj(y) : y;
+    }
+  }
+}
+
+// Real to complex: n real samples -> n/2+1 bins (fourier/numpy.py:41-43).
+// First version: transform the real data as complex with zero imaginary part.
+template <int LOG2N, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_r2c_kernel(FftArgs a) {
+  using C = FftCfg<LOG2N>;
+  cf* smem = BBT_SMEM(cf);
+  const long long blk = blockIdx.x;
+  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  const float* in = static_cast<const float*>(a.in);
+  cf* out = static_cast<cf*>(a.out);
+  const long long ibase = m.b * C::N * a.inner + m.c;
+  const long long obase = m.b * (C::N / 2 + 1) * a.inner + m.c;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) {
+    float x = 0.f;
+    if (m.valid) x = in[ibase + (long long)(m.t + C::T * e) * a.inner];
+    v[e] = mk(x, 0.f);
+  }
+  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  if (m.valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      const int k = m.t + C::T * e;
+      if (k <= C::N / 2) out[obase + (long long)k * a.inner] = cscale(v[e], a.scale);
+    }
+  }
+}
+
+// Complex to real: n/2+1 bins -> n real samples (fourier/numpy.py:46-49).
+// Like numpy's irfft the imaginary parts of bins 0 and n/2 are ignored.
+template <int LOG2N, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2r_kernel(FftArgs a) {
+  using C = FftCfg<LOG2N>;
+  cf* smem = BBT_SMEM(cf);
+  const long long blk = blockIdx.x;
+  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  const cf* in = static_cast<const cf*>(a.in);
+  float* out = static_cast<float*>(a.out);
+  const long long ibase = m.b * (C::N / 2 + 1) * a.inner + m.c;
+  const long long obase = m.b * C::N * a.inner + m.c;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) {
+    const int k = m.t + C::T * e;
+    cf x = mk(0.f, 0.f);
+    if (m.valid) {
+      if (k <= C::N / 2) {
+        x = in[ibase + (long long)k * a.inner];
+        if (k == 0 || k == C::N / 2) x.y = 0.f;
+        x = cconj(x);  // inverse transform = conj(fft(conj(X)))
+      } else {
+        x = in[ibase + (long long)(C::N - k) * a.inner];  // conj(conj(X[n-k]))
+      }
+    }
+    v[e] = x;
+  }
+  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  if (m.valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      out[obase + (long long)(m.t + C::T * e) * a.inner] = v[e].x * a.scale;
+  }
+}
+
+// Out-of-place transpose of a [rows][cols] complex matrix per batch
+// (natural-order output of the two-pass large FFT).
+BBT_GLOBAL void transpose_kernel(const cf* BBT_RESTRICT in, cf* BBT_RESTRICT out,
+                                 long long rows, long long cols) {
+  cf* tile = BBT_SMEM(cf);  // 32 x 33
+  const long long batch = blockIdx.z;
+  const cf* src = in + batch * rows * cols;
+  cf* dst = out + batch * rows * cols;
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += blockDim.y) {
+    const long long r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i * 33 + tx] = src[r * cols + c];
+  }
+  BBT_SYNC();
+  for (int i = ty; i < 32; i += blockDim.y) {
+    const long long c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[tx * 33 + i];
+  }
+}
+
+// Pointwise twiddle of the four-step FFT: a[k1][n2] *= W_N^{k1 n2} (or its
+// conjugate).  Only used by the generic large-N FFTMaker path; the
+// dedispersion plan folds this into its row kernel.
+struct BigTwiddle {
+  const cf* lo;  // exp(-2 pi i m / N), m < 8192
+  const cf* hi;  // exp(-2 pi i m 8192 / N), m < N / 8192
+  BBT_HD cf get(long long m) const {
+    cf w = ldtw(lo, (int)(m & (kTwiddleTable - 1)));
+    const long long h = m >> kLog2TwiddleTable;
+    if (h) w = cmul(w, ldtw(hi, (int)h));
+    return w;
+  }
+};
+
+BBT_GLOBAL void twiddle_kernel(cf* data, long long n1, long long n2,
+                               long long batch, BigTwiddle tw, int conj) {
+  const long long total = batch * n1 * n2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % (n1 * n2);
+    cf w = tw.get((r / n2) * (r % n2));
+    data[i] = conj ? cmulc(data[i], w) : cmul(data[i], w);
+  }
+}
+
+}  // namespace bbt

@@ -1,0 +1,141 @@
+// Thin runtime layer: device allocation, copies and kernel launches.
+//
+// Built with nvcc this maps straight onto the CUDA runtime.  Built with
+// -DBBT_EMULATE (tests/emu only) the same kernels run on host threads so that
+// index arithmetic can be checked on machines without a GPU; that build is
+// test infrastructure and is never loaded by the product package.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+
+#if defined(BBT_EMULATE)
+// --------------------------------------------------------------- emulation
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+struct bbt_emu_dim3 {
+  unsigned x, y, z;
+  bbt_emu_dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1)
+      : x(x_), y(y_), z(z_) {}
+};
+typedef bbt_emu_dim3 dim3;
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+void* bbt_emu_smem();
+void bbt_emu_syncthreads();
+#include <functional>
+void bbt_emu_launch(dim3 grid, dim3 block, size_t smem,
+                    const std::function<void()>& body);
+#define BBT_GLOBAL static
+#define BBT_DEV static inline
+#define BBT_LAUNCH_BOUNDS(t, b)
+#define BBT_SMEM(type) reinterpret_cast<type*>(bbt_emu_smem())
+#define BBT_RESTRICT __restrict__
+#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  bbt_emu_launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
+#define BBT_SET_SMEM(kernel, bytes) 0
+typedef void* bbt_stream_t;
+namespace bbt {
+inline float atomic_add(float* p, float v) {
+  uint32_t* ip = reinterpret_cast<uint32_t*>(p);
+  uint32_t old = __atomic_load_n(ip, __ATOMIC_RELAXED), nw;
+  float f;
+  do {
+    memcpy(&f, &old, 4);
+    f += v;
+    memcpy(&nw, &f, 4);
+  } while (!__atomic_compare_exchange_n(ip, &old, nw, false, __ATOMIC_RELAXED,
+                                        __ATOMIC_RELAXED));
+  return f;
+}
+inline unsigned long long atomic_add(unsigned long long* p,
+                                     unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+inline void sincospi_d(double x, double* s, double* c) {
+  *s = sin(M_PI * x);
+  *c = cos(M_PI * x);
+}
+inline double dmul(double a, double b) { return a * b; }
+inline double dadd(double a, double b) { return a + b; }
+inline double ddiv(double a, double b) { return a / b; }
+inline int dev_alloc(void** p, size_t bytes) {
+  *p = malloc(bytes ? bytes : 1);
+  return *p ? 0 : -1;
+}
+inline void dev_free(void* p) { free(p); }
+inline int h2d(void* dst, const void* src, size_t bytes, bbt_stream_t) {
+  memcpy(dst, src, bytes);
+  return 0;
+}
+inline int dev_zero(void* dst, size_t bytes, bbt_stream_t) {
+  memset(dst, 0, bytes);
+  return 0;
+}
+inline const char* launch_error() { return nullptr; }
+inline int sm_count() { return 4; }
+}  // namespace bbt
+#else
+// --------------------------------------------------------------------- CUDA
+#include <cuda_runtime.h>
+#define BBT_GLOBAL __global__
+#define BBT_DEV __device__ __forceinline__
+#define BBT_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define BBT_SMEM(type) reinterpret_cast<type*>(bbt_dyn_smem)
+#define BBT_RESTRICT __restrict__
+#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define BBT_SET_SMEM(kernel, bytes)                                         \
+  ((bytes) > 48 * 1024                                                      \
+       ? (int)cudaFuncSetAttribute(                                         \
+             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)) \
+       : 0)
+typedef cudaStream_t bbt_stream_t;
+extern __shared__ float4 bbt_dyn_smem[];
+namespace bbt {
+__device__ __forceinline__ float atomic_add(float* p, float v) {
+  return atomicAdd(p, v);
+}
+__device__ __forceinline__ unsigned long long atomic_add(
+    unsigned long long* p, unsigned long long v) {
+  return atomicAdd(p, v);
+}
+__device__ __forceinline__ void sincospi_d(double x, double* s, double* c) {
+  sincospi(x, s, c);
+}
+// Explicitly rounded double arithmetic (no FMA contraction): the fold-bin
+// assignment must match the oracle's numpy float64 operations bit for bit.
+__device__ __forceinline__ double dmul(double a, double b) {
+  return __dmul_rn(a, b);
+}
+__device__ __forceinline__ double dadd(double a, double b) {
+  return __dadd_rn(a, b);
+}
+__device__ __forceinline__ double ddiv(double a, double b) {
+  return __ddiv_rn(a, b);
+}
+inline int dev_alloc(void** p, size_t bytes) {
+  return (int)cudaMalloc(p, bytes ? bytes : 1);
+}
+inline void dev_free(void* p) { cudaFree(p); }
+inline int h2d(void* dst, const void* src, size_t bytes, bbt_stream_t s) {
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+inline int dev_zero(void* dst, size_t bytes, bbt_stream_t s) {
+  return (int)cudaMemsetAsync(dst, 0, bytes, s);
+}
+inline const char* launch_error() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+inline int sm_count() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+}  // namespace bbt
+#endif

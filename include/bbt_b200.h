@@ -1,0 +1,150 @@
+/* bbt_b200.h -- C ABI of the B200 baseband-tasks hot path.
+ *
+ * The reference (mhvk/baseband-tasks) is pure Python and has no FFI; this ABI
+ * is the boundary a drop-in replacement of its hot path exports.  Each entry
+ * point names the reference code it replaces (paths relative to
+ * baseband_tasks/ in the reference tree).  The Python side binds it with
+ * ctypes (baseband_tasks_b200/_cabi.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative bbt_status on failure;
+ *    bbt_last_error() gives a thread-local message; nothing throws or aborts;
+ *  - all data pointers are DEVICE pointers owned by the caller (complex64 =
+ *    interleaved float re,im; time-major, C-contiguous, as Base.read()
+ *    delivers them, base.py:389-438) unless a parameter says "host";
+ *  - the library allocates only opaque plan objects (twiddle/chirp tables),
+ *    created and destroyed explicitly; plans are immutable after creation and
+ *    bound to the device that was current at creation;
+ *  - every launch takes a cudaStream_t (as void*) and never synchronises.
+ */
+#ifndef BBT_B200_H
+#define BBT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum bbt_status {
+  BBT_OK = 0,
+  BBT_EINVAL = -1,      /* bad argument (ValueError on the Python side) */
+  BBT_EUNSUPPORTED = -2,/* size/shape outside what the kernels handle */
+  BBT_ECUDA = -3,       /* CUDA runtime error */
+  BBT_ENOMEM = -4
+};
+
+enum bbt_fft_kind { BBT_C2C = 0, BBT_R2C = 1, BBT_C2R = 2 };
+enum bbt_fft_direction { BBT_FORWARD = 0, BBT_BACKWARD = 1 };
+
+typedef struct bbt_fft_plan bbt_fft_plan;
+typedef struct bbt_dedisperse_plan bbt_dedisperse_plan;
+
+int bbt_version(void);
+const char* bbt_last_error(void);
+
+/* ---- FFT: replaces np.fft.{fft,ifft,rfft,irfft}(a, axis, norm) as called by
+ * NumpyFFTBase (fourier/numpy.py:33-49) for the FFT objects FFTMakerBase.__call__
+ * creates (fourier/base.py:262-311).  Data are [outer][n][inner]; the
+ * transform runs along the middle axis.  n must be a power of two; n > 8192
+ * needs inner == 1 and a work buffer of bbt_fft_plan_work_bytes().
+ * scale multiplies the output (1, 1/n or 1/sqrt(n): fourier/base.py:95-104). */
+int bbt_fft_plan_create(bbt_fft_plan** plan, int64_t n, int64_t outer,
+                        int64_t inner, int kind, int direction, double scale);
+int64_t bbt_fft_plan_work_bytes(const bbt_fft_plan* plan);
+int bbt_fft_exec(const bbt_fft_plan* plan, const void* in, void* out,
+                 void* work, void* stream);
+int bbt_fft_plan_destroy(bbt_fft_plan* plan);
+
+/* ---- Coherent (de)dispersion: replaces Disperse.task, i.e.
+ * ifft(fft(x) * phase_factor)[pad_start : pad_start + n_valid]
+ * (dispersion.py:115-139) over whole runs of overlap-save frames
+ * (base.py:775-795).  Frames are [n][n_series] complex64.
+ * The chirp is generated on the device in float64 from
+ *   phase = K dm F (1/f_ref - 1/F)^2 1e6 sideband + sample_offset/rate fftfreq,
+ *   F = freq + fftfreq sideband      (dm.py:103-105, dispersion.py:117-126)
+ * with one (freq, f_ref, sideband) triple per distinct chirp; series_map[s]
+ * (host, n_series ints) says which chirp series s uses.  dm is the dispersing
+ * DM (Dedisperse passes -dm, dispersion.py:184).  log2n1_hint selects the
+ * column-FFT length of the three-pass split (0 = automatic). */
+int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
+                               int64_t n_series, int64_t pad_start,
+                               int64_t n_valid, int64_t n_chirp,
+                               const int32_t* series_map,
+                               const double* freq_mhz, const double* fref_mhz,
+                               const int8_t* sideband, double dm,
+                               double rate_mhz, double sample_offset,
+                               int log2n1_hint);
+/* Replace the chirp by an arbitrary response (host, [n_chirp][n] complex64,
+ * natural FFT bin order): Convolve-style reuse (convolution.py:97-119). */
+int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* plan,
+                                     const void* host_response);
+/* Copy the chirp back to the host in natural bin order ([n_chirp][n]). */
+int bbt_dedisperse_plan_get_response(const bbt_dedisperse_plan* plan,
+                                     void* host_response);
+int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* plan,
+                                  int64_t n_frames);
+/* Frame f reads in + f*in_frame_stride (complex elements) and writes its
+ * n_valid - skip samples [pad_start+skip, pad_start+n_valid) to
+ * out + f*out_frame_stride.  skip is PaddedTaskBase._frame_offset of a
+ * re-anchored last frame (base.py:783-795); 0 otherwise. */
+int bbt_dedisperse_exec(const bbt_dedisperse_plan* plan, const void* in,
+                        int64_t in_frame_stride, int64_t n_frames,
+                        int64_t skip, void* out, int64_t out_frame_stride,
+                        void* work, void* stream);
+int bbt_dedisperse_plan_destroy(bbt_dedisperse_plan* plan);
+
+/* ---- Detection: replaces Power.task (functions.py:132-143) on (A, 2, B)
+ * complex64 -> (A, 4, B) float32, and Square.task (functions.py:15-16,41). */
+int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
+                   void* stream);
+int bbt_square_exec(const void* in, void* out, int64_t n, int is_complex,
+                    void* stream);
+
+/* ---- Fused Channelize(n) -> Power: replaces channelize.py:73-74 followed by
+ * functions.py:132-143 for input [(n_spec*n)][m][2] complex64 -> output
+ * [n_spec][n][m][4] float32. */
+int bbt_channelize_power_exec(const void* in, void* out, int64_t n, int64_t m,
+                              int64_t n_spec, void* stream);
+/* ... -> Integrate: additionally integration.py:273-303.  offsets (device,
+ * int64) are absolute bin edges in spectra; bins b_first .. b_first+n_bins-1
+ * are accumulated (+=) into sum[bin][n][m][4] (float32) and count[bin]
+ * (int64) for the part that overlaps spectra [j_first, j_first + n_spec). */
+int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
+                                        int64_t n_spec, int64_t j_first,
+                                        const int64_t* offsets,
+                                        int64_t b_first, int64_t n_bins,
+                                        void* sum, void* count, void* stream);
+
+/* ---- Integrate: replaces Integrate._integrate (integration.py:273-303) for
+ * float32 input [n][inner]; same offsets/accumulate convention as above. */
+int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
+                       int64_t i_first, const int64_t* offsets,
+                       int64_t b_first, int64_t n_bins, void* sum, void* count,
+                       void* stream);
+
+/* ---- Fold: replaces Fold._integrate (integration.py:380-395).  Time bin b
+ * covers absolute samples [lo[b], hi[b]) (device int64; the host applies the
+ * reference's searchsorted convention).  Phase bins come either from pbin
+ * (device int32 per sample of this call) or from the float64 polynomial
+ * phase(i) = sum_k coef[k] ((i - i_ref)/rate)^k evaluated by Horner's rule
+ * with individually rounded operations.  With power != 0 the input is
+ * [n][inner/4][2] complex64 and the four polarization products are formed
+ * on the fly.  sum[bin][n_phase][inner] float32 and count[bin][n_phase]
+ * int64 are accumulated (+=). */
+int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
+                  int64_t i_first, const int64_t* lo, const int64_t* hi,
+                  int64_t b_first, int64_t n_bins, const int32_t* pbin,
+                  const double* coef, int ncoef, int64_t i_ref, double rate,
+                  int n_phase, void* sum, void* count, void* stream);
+
+/* ---- Measurement helper (not part of the reference surface): copies
+ * `rows` chunks of chunk_bytes, row_stride_bytes apart, for each of n_tiles
+ * column tiles -- the access pattern of the strided FFT passes. */
+int bbt_strided_copy_bench(const void* in, void* out, int64_t rows,
+                           int64_t row_stride_bytes, int64_t chunk_bytes,
+                           int64_t n_tiles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBT_B200_H */
