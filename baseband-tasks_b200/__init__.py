@@ -1,3 +1,22 @@
 """B200-native implementation of the baseband-tasks dedispersion and
-channelization hot path, behind the baseband-tasks Task / FFTMaker API."""
+channelization hot path, behind the baseband-tasks Task / FFTMaker API.
+
+Python host code calls hand-written sm_100a CUDA kernels through the C ABI in
+``include/bbt_b200.h``; PyTorch is used only for device buffers and streams.
+There is no CPU fallback: using a task without the built CUDA library or
+without a GPU raises.
+"""
 __version__ = '0.1'
+
+from . import _cabi  # noqa: F401
+from .base import (Base, BaseTaskBase, TaskBase, PaddedTaskBase, Task,  # noqa
+                   SetAttribute)
+from ._units import Time  # noqa: F401
+from .fourier import fft_maker, CudaFFTMaker  # noqa: F401
+from .dm import DispersionMeasure  # noqa: F401
+from .dispersion import Disperse, Dedisperse  # noqa: F401
+from .channelize import Channelize, Dechannelize  # noqa: F401
+from .functions import Square, Power  # noqa: F401
+from .integration import Integrate, Fold, PolynomialPhase  # noqa: F401
+from .generators import (StreamGenerator, EmptyStreamGenerator, Noise,  # noqa
+                         NoiseGenerator, ArrayStream)

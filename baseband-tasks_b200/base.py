@@ -1,0 +1,691 @@
+"""Task framework: the reference's stream API with device-resident chaining.
+
+Mirrors baseband_tasks/base.py of the reference (``Base`` :87, ``BaseTaskBase``
+:499, ``TaskBase`` :613, ``PaddedTaskBase`` :709, ``Task`` :798,
+``SetAttribute`` :892): same constructor arguments, properties
+(``shape``, ``sample_shape``, ``samples_per_frame``, ``dtype``,
+``sample_rate``, ``start_time``/``time``/``stop_time``, ``frequency``,
+``sideband``, ``polarization``), ``read``/``seek``/``tell``/``close`` and the
+same exceptions.
+
+What is new: frames of tasks that run on the GPU are device tensors, and a
+task reads its input with ``read_device`` so data stay in HBM between tasks
+(the reference copies every frame through numpy, base.py:431-433).  Tasks whose
+kernels take whole runs of frames (``_run_frames``) process many frames per
+launch and write straight into the caller's buffer; the result of every frame
+is the same as when frames are processed one at a time.
+"""
+import inspect
+import operator
+import types
+import warnings
+
+import numpy as np
+
+from . import _buffers as B
+from ._units import to_float
+
+__all__ = ['Base', 'BaseTaskBase', 'TaskBase', 'PaddedTaskBase',
+           'SetAttribute', 'Task', 'META_ATTRIBUTES', 'check_broadcast_to',
+           'simplify_shape', 'getattr_if_none']
+
+META_ATTRIBUTES = {'frequency', 'sideband', 'polarization'}
+
+# Target size of the blocks of frames device tasks process per launch.
+BLOCK_BYTES = 1 << 30
+
+
+def check_broadcast_to(value, sample_shape):
+    """`numpy.broadcast_to` with a clearer error (base.py:24-34)."""
+    try:
+        broadcast = np.broadcast_to(value, sample_shape, subok=True)
+    except ValueError as exc:
+        exc.args += ("value cannot be broadcast to sample shape",)
+        raise
+    return broadcast
+
+
+def simplify_shape(value):
+    """Drop axes along which all entries are equal (base.py:37-53)."""
+    for axis in range(value.ndim):
+        value_0 = value[(slice(None),) * axis + (slice(0, 1),)]
+        if value.strides[axis] == 0 or np.all(value == value_0):
+            value = value_0
+    first_not_unity = next((i for (i, s) in enumerate(value.shape)
+                            if s > 1), value.ndim)
+    return value.reshape(value.shape[first_not_unity:]).copy()
+
+
+def getattr_if_none(ih, attr, value=None, *, required=True, **kwargs):
+    """`getattr` used only if no value was passed in (base.py:56-84)."""
+    if value is None:
+        value = kwargs.get(attr, None)
+        if value is None:
+            value = getattr(ih, attr, None)
+    if required and value is None:
+        raise TypeError(f"{attr!r} should either be defined by the "
+                        "underlying stream or passed in.")
+    return value
+
+
+def _copy_meta(meta):
+    return {k: (dict(v) if isinstance(v, dict) else v)
+            for k, v in dict(meta).items()}
+
+
+class Base:
+    """Base class of all tasks and generators (base.py:87-496).
+
+    Subclasses define ``_read_frame(frame_index)``, returning one frame as a
+    numpy array (host tasks, generators) or a device tensor (GPU tasks).
+    """
+    offset = 0
+    _frame_index = None
+    _frame = None
+    closed = False
+
+    def __init__(self, shape, start_time, sample_rate, *,
+                 samples_per_frame=1, dtype=np.complex64, **kwargs):
+        self._shape = tuple(shape)
+        self._start_time = start_time
+        self._samples_per_frame = operator.index(samples_per_frame)
+        self._sample_rate = sample_rate
+        self._dtype = np.dtype(dtype)
+        if 'meta' not in self.__dict__:
+            self.meta = {}
+
+        if len({'frequency', 'sideband'}.difference(kwargs)) == 1:
+            raise ValueError('frequency and sideband should both '
+                             'be passed in.')
+
+        attributes = {}
+        for attr, value in kwargs.items():
+            if attr in META_ATTRIBUTES:
+                if value is not None:
+                    if attr == 'sideband':
+                        value = np.where(np.asanyarray(value) > 0,
+                                         np.int8(1), np.int8(-1))
+                    attributes[attr] = self._check_shape(value)
+            else:
+                raise TypeError('__init__() got unexpected keyword argument '
+                                f'{attr!r}')
+        if attributes:
+            self.meta.setdefault('__attributes__', {}).update(attributes)
+
+    def __getattr__(self, attr):
+        if attr in META_ATTRIBUTES:
+            meta = self.__dict__.get('meta', {})
+            value = meta.get('__attributes__', {}).get(attr, None)
+            if value is None:
+                raise AttributeError(f"{attr} not set.")
+            return value
+        raise AttributeError(f"{type(self).__name__!r} object has no "
+                             f"attribute {attr!r}")
+
+    def __dir__(self):
+        return sorted(META_ATTRIBUTES.union(super().__dir__()))
+
+    # ---------------------------------------------------------------- repr
+    def _repr_item(self, key, default, value=None):
+        if value is None:
+            value = getattr(self, key, None)
+            if value is None:
+                value = getattr(self, '_' + key, None)
+                if value is None:
+                    return None
+        if default is not inspect._empty:
+            try:
+                if np.all(value == default):
+                    return None
+            except Exception:
+                pass
+        return f"{key}={value}".replace('\n', ',')
+
+    def __repr__(self):
+        name = self.__class__.__name__
+        pars = {}
+        for cls in self.__class__.__mro__:
+            for key, par in inspect.signature(cls).parameters.items():
+                pars.setdefault(key, par)
+            if 'kwargs' not in pars or cls is Base:
+                break
+        overrides = [self._repr_item(key, par.default)
+                     for key, par in pars.items()]
+        if cls is Base and '__attributes__' in self.meta:
+            overrides.extend([self._repr_item(key, None)
+                              for key in self.meta['__attributes__'].keys()
+                              if key not in pars])
+        overrides = (',\n ' + ' ' * len(name)).join(
+            [override for override in overrides if override])
+        return f"{name}({overrides})"
+
+    # ---------------------------------------------------------- properties
+    def _check_shape(self, value):
+        """Check that value can be broadcast to the sample shape."""
+        broadcast = check_broadcast_to(value, self.sample_shape)
+        return simplify_shape(broadcast)
+
+    @property
+    def shape(self):
+        """Shape of the output."""
+        return self._shape
+
+    @property
+    def sample_shape(self):
+        """Shape of a complete sample."""
+        return self.shape[1:]
+
+    @property
+    def samples_per_frame(self):
+        """Number of samples per frame of data."""
+        return self._samples_per_frame
+
+    @property
+    def size(self):
+        """Number of component samples in the output."""
+        prod = 1
+        for dim in self.shape:
+            prod *= dim
+        return prod
+
+    @property
+    def ndim(self):
+        """Number of dimensions of the output."""
+        return len(self.shape)
+
+    @property
+    def dtype(self):
+        """Data type of the output."""
+        return self._dtype
+
+    @property
+    def complex_data(self):
+        return self._dtype.kind == 'c'
+
+    @property
+    def sample_rate(self):
+        """Number of complete samples per second."""
+        return self._sample_rate
+
+    @property
+    def start_time(self):
+        """Start time of the output."""
+        return self._tell_time(0)
+
+    @property
+    def time(self):
+        """Time of the sample pointer's current offset in the output."""
+        return self._tell_time(self.offset)
+
+    @property
+    def stop_time(self):
+        """Time at the end of the output, just after the last sample."""
+        return self._tell_time(self.shape[0])
+
+    # --------------------------------------------------------- positioning
+    def seek(self, offset, whence=0):
+        """Change the sample pointer position (base.py:312-353).
+
+        ``offset`` is a number of samples, a time offset or an absolute time;
+        for the latter two the pointer moves to the nearest sample.
+        """
+        try:
+            offset = operator.index(offset)
+        except Exception:
+            try:
+                offset = offset - self.start_time
+            except Exception:
+                pass
+            else:
+                whence = 0
+            offset = int(np.round(to_float(offset * self.sample_rate)))
+
+        if whence == 0 or whence == 'start':
+            self.offset = offset
+        elif whence == 1 or whence == 'current':
+            self.offset += offset
+        elif whence == 2 or whence == 'end':
+            self.offset = self.shape[0] + offset
+        else:
+            raise ValueError("invalid 'whence'; should be 0 or 'start', 1 or "
+                             "'current', or 2 or 'end'.")
+        return self.offset
+
+    def tell(self, unit=None):
+        """Current offset: samples, a time offset, or (``'time'``) the time."""
+        if unit is None:
+            return self.offset
+        if isinstance(unit, str) and unit == 'time':
+            return self._tell_time(self.offset)
+        elapsed = self.offset / self.sample_rate
+        return elapsed.to(unit) if hasattr(elapsed, 'to') else elapsed
+
+    def _tell_time(self, offset):
+        return self._start_time + offset / self.sample_rate
+
+    # -------------------------------------------------------------- reading
+    def read(self, count=None, out=None):
+        """Read a number of complete samples into a numpy array.
+
+        Same contract as the reference (base.py:389-438): ``count`` samples
+        (default: all that are left) or ``out.shape[0]``; ``EOFError`` beyond
+        the end, ``ValueError`` on a closed stream.  The caller owns the
+        returned array.
+        """
+        count = self._check_read(count, out)
+        data = self._read_data(count)
+        if out is None:
+            if B.is_tensor(data):
+                return data.cpu().numpy()
+            return np.array(data, copy=True)
+        out[...] = B.as_host(data)
+        return out
+
+    def read_device(self, count=None):
+        """Like `read`, but returns a device tensor and never leaves HBM.
+
+        The tensor may alias an internal frame buffer: consume it before the
+        next read of this stream and do not modify it.
+        """
+        count = self._check_read(count, None)
+        return B.as_device(self._read_data(count))
+
+    def _check_read(self, count, out):
+        if self.closed:
+            raise ValueError("I/O operation on closed stream.")
+        samples_left = self.shape[0] - self.offset
+        if out is None:
+            if count is None or count < 0:
+                count = max(0, samples_left)
+        else:
+            assert out.shape[1:] == self.sample_shape, (
+                "'out' must have trailing shape {}".format(self.sample_shape))
+            count = out.shape[0]
+        if count > samples_left:
+            raise EOFError("cannot read from beyond end of input.")
+        return count
+
+    def _read_data(self, count, out=None):
+        """Samples [offset, offset+count) from cached frames (base.py:425-438).
+
+        Returns a view of the frame when one frame covers the request.
+        """
+        offset0 = self.offset
+        sample = 0
+        result = out
+        while sample < count:
+            frame, sample_offset = self._get_frame(self.offset)
+            nsample = min(count - sample, len(frame) - sample_offset)
+            data = frame[sample_offset:sample_offset + nsample]
+            if result is None:
+                if nsample == count:
+                    self.offset = offset0 + count
+                    return data
+                result = _empty_like(data, (count,) + tuple(data.shape[1:]))
+            result[sample:sample + nsample] = data
+            sample += nsample
+            self.offset = offset0 + sample
+        if result is None:
+            result = np.empty((0,) + self.sample_shape, self.dtype)
+        return result
+
+    def _get_frame(self, offset):
+        """Frame holding ``offset`` and the offset in it (base.py:440-467)."""
+        frame_index, sample_offset = divmod(offset, self.samples_per_frame)
+        if frame_index != self._frame_index:
+            self.offset = frame_index * self.samples_per_frame
+            self._frame = self._read_frame(frame_index)
+            self._frame_index = frame_index
+        return self._frame, sample_offset
+
+    def __getitem__(self, item):
+        from .shaping import GetSlice
+        return GetSlice(self, item)
+
+    def __array__(self, dtype=None, copy=None):
+        old_offset = self.tell()
+        try:
+            self.seek(0)
+            return np.array(self.read(), dtype=dtype)
+        finally:
+            self.seek(old_offset)
+
+    def __array_ufunc__(self, *args, **kwargs):
+        return NotImplemented
+
+    def __array_function__(self, *args, **kwargs):
+        return NotImplemented
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.close()
+
+    def close(self):
+        self.closed = True
+        self._frame = None
+        self._frame_index = None
+
+
+def _empty_like(data, shape):
+    if B.is_tensor(data):
+        return data.new_empty(shape)
+    return np.empty(shape, data.dtype)
+
+
+class BaseTaskBase(Base):
+    """Base for all classes that operate on underlying streams
+    (base.py:499-610).  By default, all parameters are taken from ``ih``."""
+
+    def __init__(self, ih, *, ih_samples_per_frame=None,
+                 start_time=None, shape=None, sample_rate=None,
+                 samples_per_frame=None, dtype=None, **kwargs):
+        self.ih = ih
+        if ih_samples_per_frame is None:
+            ih_samples_per_frame = ih.samples_per_frame
+        self._ih_samples_per_frame = ih_samples_per_frame
+
+        shape = getattr_if_none(ih, 'shape', shape)
+        start_time = getattr_if_none(ih, 'start_time', start_time)
+        sample_rate = getattr_if_none(ih, 'sample_rate', sample_rate)
+        dtype = getattr_if_none(ih, 'dtype', dtype)
+        if samples_per_frame is None:
+            samples_per_frame = ih_samples_per_frame
+
+        self.meta = _copy_meta(getattr(ih, 'meta', {}))
+        for attr in META_ATTRIBUTES:
+            value = getattr_if_none(ih, attr, kwargs.pop(attr, None),
+                                    required=False)
+            if value is not None:
+                kwargs[attr] = value
+
+        super().__init__(shape=shape, start_time=start_time,
+                         sample_rate=sample_rate,
+                         samples_per_frame=samples_per_frame,
+                         dtype=dtype, **kwargs)
+
+    def _repr_item(self, key, default, value=None):
+        if key == 'ih':
+            return 'ih'
+        if default is None:
+            if key == 'samples_per_frame':
+                default = self._ih_samples_per_frame
+            elif key == 'ih_samples_per_frame':
+                default = self.ih.samples_per_frame
+            else:
+                default = getattr(self.ih, key, None)
+        return super()._repr_item(key, default=default, value=value)
+
+    def __repr__(self):
+        base = super().__repr__()
+        if base.count('\n') == 1:
+            base = ' '.join(b.strip() for b in base.split('\n'))
+        return (base + "\nih: "
+                + "\n    ".join(repr(self.ih).split('\n')))
+
+    def _ih_read(self, start, count, device=None):
+        """Input samples [start, start+count) as the task wants them."""
+        self.ih.seek(start)
+        if device is None:
+            device = getattr(self, '_on_device', False)
+        if device:
+            if hasattr(self.ih, 'read_device'):
+                return self.ih.read_device(count)
+            return B.as_device(self.ih.read(count))
+        return self.ih.read(count)
+
+    def close(self):
+        """Close task; the underlying stream is only dereferenced."""
+        super().close()
+        del self.ih
+
+
+class TaskBase(BaseTaskBase):
+    """Base class of all tasks (base.py:613-706).
+
+    Subclasses define ``task(data)``, which turns the input samples of one
+    frame into its output samples.  GPU tasks set ``_on_device = True`` and
+    get and return device tensors; those whose ``task`` handles any whole
+    number of frames at once also set ``_multi_frame = True``.
+    """
+    _on_device = False
+    _multi_frame = False
+
+    def __init__(self, ih, *, ih_samples_per_frame=None,
+                 shape=None, sample_rate=None, samples_per_frame=None,
+                 **kwargs):
+        if sample_rate is None:
+            sample_rate = ih.sample_rate
+            sample_rate_ratio = 1.
+        else:
+            sample_rate_ratio = to_float(ih.sample_rate / sample_rate)
+        if samples_per_frame is None:
+            if ih_samples_per_frame is None:
+                ih_samples_per_frame = ih.samples_per_frame
+            samples_per_frame = ih_samples_per_frame / sample_rate_ratio
+            assert samples_per_frame % 1 == 0, (
+                "inferred samples per frame must be integer")
+            samples_per_frame = int(samples_per_frame)
+        elif ih_samples_per_frame is None:
+            ih_samples_per_frame = samples_per_frame * sample_rate_ratio
+            assert ih_samples_per_frame % 1 == 0, (
+                "inferred input samples per frame must be integer")
+            ih_samples_per_frame = int(ih_samples_per_frame)
+
+        assert ih_samples_per_frame <= ih.shape[0], (
+            "time per frame larger than total time in stream")
+
+        if shape is None or shape[0] == -1:
+            ns = ((ih.shape[0] // ih_samples_per_frame)
+                  * samples_per_frame)
+            shape = (ns,) + (ih.shape[1:] if shape is None
+                             else tuple(shape[1:]))
+
+        super().__init__(ih=ih, ih_samples_per_frame=ih_samples_per_frame,
+                         shape=shape, sample_rate=sample_rate,
+                         samples_per_frame=samples_per_frame,
+                         **kwargs)
+        alignment = max(1, int(sample_rate_ratio))
+        self._ih_stop = (self.ih.shape[0] // alignment) * alignment
+
+    def _seek_frame(self, frame_index):
+        return self.ih.seek(frame_index * self._ih_samples_per_frame)
+
+    def _read_frame(self, frame_index):
+        start = self._seek_frame(frame_index)
+        stop = min(start + self._ih_samples_per_frame, self._ih_stop)
+        data = self._ih_read(start, stop - start)
+        return self.task(data)
+
+    # Whole runs of frames per launch, for tasks that can (``_multi_frame``).
+    def _frames_per_block(self):
+        per_frame = max(1, self.samples_per_frame * self._dtype.itemsize
+                        * int(np.prod(self.sample_shape, dtype=np.int64)))
+        return max(1, BLOCK_BYTES // per_frame)
+
+    def _run_frames(self, f0, f1, out=None):
+        """Output of frames f0..f1-1 (all complete), optionally into ``out``."""
+        start = f0 * self._ih_samples_per_frame
+        stop = min(f1 * self._ih_samples_per_frame, self._ih_stop)
+        data = self._ih_read(start, stop - start)
+        return self.task(data, out=out) if out is not None else self.task(data)
+
+    def _read_data(self, count, out=None):
+        if not (self._on_device and self._multi_frame) or count == 0:
+            return super()._read_data(count, out)
+        spf = self.samples_per_frame
+        a = self.offset
+        b = a + count
+        n_complete = self.shape[0] // spf   # frames with all spf samples
+        result = out
+        pos = a
+        while pos < b:
+            f = pos // spf
+            f_end = min(b // spf, n_complete)
+            if result is None and pos == a == f * spf:
+                # Whole request from one launch over the frames covering it
+                # (the unused tail of the last frame is simply not returned).
+                f_cover = -(-b // spf)
+                if (f_cover <= n_complete
+                        and f_cover - f <= self._frames_per_block()):
+                    self.offset = b
+                    return self._run_frames(f, f_cover)[:count]
+            if pos == f * spf and f < f_end:
+                # A run of complete frames: straight into the result.
+                f_end = min(f_end, f + self._frames_per_block())
+                n = (f_end - f) * spf
+                if result is None and pos == a and n == count:
+                    self.offset = b
+                    return self._run_frames(f, f_end)
+                if result is None:
+                    result = B.empty((count,) + self.sample_shape, self.dtype)
+                self._run_frames(f, f_end, out=result[pos - a:pos - a + n])
+            else:
+                frame, sample_offset = self._get_frame(pos)
+                n = min(b - pos, len(frame) - sample_offset)
+                data = frame[sample_offset:sample_offset + n]
+                if result is None and n == count:
+                    self.offset = b
+                    return data
+                if result is None:
+                    result = B.empty((count,) + self.sample_shape, self.dtype)
+                result[pos - a:pos - a + n] = data
+            pos += n
+            self.offset = pos
+        return result
+
+
+class PaddedTaskBase(TaskBase):
+    """Base for tasks which need more points than they produce
+    (overlap-save framing, base.py:709-795).
+
+    Frame ``i`` reads ``samples_per_frame + pad_start + pad_end`` input samples
+    starting at ``i * samples_per_frame``; a last, partial frame is re-anchored
+    to the end of the input and ``_frame_offset`` samples of it are skipped.
+    """
+
+    def __init__(self, ih, pad_start=0, pad_end=0, *,
+                 samples_per_frame=None, next_fast_len=None, **kwargs):
+        self._pad_start = operator.index(pad_start)
+        self._pad_end = operator.index(pad_end)
+        if self._pad_start < 0 or self._pad_end < 0:
+            raise ValueError("padding values must be 0 or positive.")
+
+        pad = self._pad_start + self._pad_end
+        if samples_per_frame is None:
+            ih_samples_per_frame = max(ih.samples_per_frame, pad * 4)
+        else:
+            ih_samples_per_frame = samples_per_frame + pad
+
+        if next_fast_len:
+            ih_samples_per_frame = next_fast_len(ih_samples_per_frame)
+
+        samples_per_frame = ih_samples_per_frame - pad
+
+        if pad > samples_per_frame:
+            warnings.warn("task will be inefficient; for {} samples "
+                          "per frame, more ({}) will be added for padding."
+                          .format(samples_per_frame, pad))
+
+        n_sample = ih.shape[0] - pad
+        shape = (n_sample,) + tuple(ih.sample_shape)
+        kwargs['start_time'] = (getattr_if_none(ih, 'start_time', **kwargs)
+                                + self._pad_start / ih.sample_rate)
+        super().__init__(ih, ih_samples_per_frame=ih_samples_per_frame,
+                         shape=shape, samples_per_frame=samples_per_frame,
+                         **kwargs)
+
+    _frame_offset = 0
+
+    def _seek_frame(self, frame_index):
+        ih_index = frame_index * self.samples_per_frame
+        max_start = self.ih.shape[0] - self._ih_samples_per_frame
+        if ih_index > max_start:
+            self._frame_offset = ih_index - max_start
+            return self.ih.seek(max_start)
+        else:
+            self._frame_offset = 0
+            return self.ih.seek(ih_index)
+
+    def _get_frame(self, offset):
+        self._frame, sample_offset = super()._get_frame(offset)
+        return self._frame, sample_offset + self._frame_offset
+
+    def _run_frames(self, f0, f1, out=None):
+        # Complete frames f0..f1-1 read input [f0*spf, (f1-1)*spf + N).
+        spf = self.samples_per_frame
+        start = f0 * spf
+        count = (f1 - 1 - f0) * spf + self._ih_samples_per_frame
+        data = self._ih_read(start, count)
+        return self.task_frames(data, f1 - f0, out=out)
+
+
+class Task(TaskBase):
+    """Apply a user-supplied callable to a stream (base.py:798-889).
+
+    The callable runs on the host with numpy arrays, as in the reference.
+    """
+
+    def __init__(self, ih, task, method=None, **kwargs):
+        if method is None:
+            try:
+                argspec = inspect.getfullargspec(task)
+                narg = len(argspec.args)
+                if argspec.defaults:
+                    narg -= len(argspec.defaults)
+                if inspect.ismethod(task):
+                    narg -= 1
+                assert 1 <= narg <= 2
+                method = narg == 2
+            except Exception as exc:
+                exc.args += ("cannot determine whether ``task`` is a "
+                             "function or method. Pass in ``method``.",)
+                raise
+
+        if method:
+            self.task = types.MethodType(task, self)
+        else:
+            self.task = task
+
+        super().__init__(ih, **kwargs)
+
+    def _repr_item(self, key, default, value=None):
+        if key == 'task' and isinstance(self.task, types.MethodType):
+            value = self.task.__func__
+        return super()._repr_item(key, default=default, value=value)
+
+
+class SetAttribute(TaskBase):
+    """Wrapper that sets or changes attributes of a stream (base.py:892-951).
+
+    When only metadata are overridden reads pass straight through to ``ih``
+    (also for ``read_device``), so the wrapper is free in a device chain.
+    """
+
+    def __init__(self, ih, *, start_time=None, sample_rate=None,
+                 **kwargs):
+        super().__init__(ih, start_time=start_time, sample_rate=sample_rate,
+                         **kwargs)
+        if not set(kwargs).difference(META_ATTRIBUTES):
+            self.read = self.simple_read
+            self.read_device = self.simple_read_device
+
+    def simple_read(self, *args, **kwargs):
+        """Read data from the underlying stream at the current offset."""
+        self.ih.seek(self.offset)
+        out = self.ih.read(*args, **kwargs)
+        self.offset = self.ih.tell()
+        return out
+
+    def simple_read_device(self, count=None):
+        self.ih.seek(self.offset)
+        if hasattr(self.ih, 'read_device'):
+            out = self.ih.read_device(count)
+        else:
+            out = B.as_device(self.ih.read(count))
+        self.offset = self.ih.tell()
+        return out
+
+    def task(self, data):
+        return data

@@ -1,6 +1,7 @@
 // C-ABI implementation (see include/bbt_b200.h) and plan objects.
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <map>
@@ -14,6 +15,53 @@
 #include "kernels_fft.cuh"
 
 using namespace bbt;
+
+// ------------------------------------------------- launch count and profiling
+namespace bbt {
+thread_local const char* prof_next_name = nullptr;
+namespace prof {
+std::mutex g_prof_mu;
+long long g_launches = 0;
+bool g_prof_on = false;
+#if !defined(BBT_EMULATE)
+struct ProfRec {
+  std::string name;
+  cudaEvent_t e0, e1;
+};
+std::vector<ProfRec> g_prof_recs;
+thread_local ProfRec* g_prof_open = nullptr;
+thread_local cudaStream_t g_prof_stream = nullptr;
+#endif
+}  // namespace prof
+using namespace prof;
+void prof_count() {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ++g_launches;
+}
+#if !defined(BBT_EMULATE)
+void prof_begin(const char* name, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec();
+  r->name = name;
+  // Template arguments are not part of the stringified name; keep it short.
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, stream);
+  g_prof_open = r;
+  g_prof_stream = stream;
+}
+void prof_end() {
+  if (!g_prof_open) return;
+  cudaEventRecord(g_prof_open->e1, g_prof_stream);
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_recs.push_back(*g_prof_open);
+  }
+  delete g_prof_open;
+  g_prof_open = nullptr;
+}
+#endif
+}  // namespace bbt
 
 namespace {
 
@@ -109,6 +157,8 @@ int launch_fft(int kind, const FftArgs& a, bbt_stream_t st) {
                                 : fft_c2r_kernel<L, LANEFAST>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = kind == BBT_C2C ? "fft_c2c" : kind == BBT_R2C ? "fft_r2c"
+                                                                 : "fft_c2r";
   BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a);
   return check_launch("fft kernel");
 }
@@ -151,6 +201,50 @@ struct bbt_dedisperse_plan {
 extern "C" {
 
 int bbt_version(void) { return 100; }
+
+int64_t bbt_launch_count(void) {
+  std::lock_guard<std::mutex> lock(bbt::prof::g_prof_mu);
+  return bbt::prof::g_launches;
+}
+
+int bbt_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(bbt::prof::g_prof_mu);
+  bbt::prof::g_prof_on = on != 0;
+  return BBT_OK;
+}
+
+int bbt_profile_report(char* buf, int64_t size) {
+  if (!buf || size < 1) return fail(BBT_EINVAL, "null buffer");
+  std::string text;
+#if !defined(BBT_EMULATE)
+  std::map<std::string, std::pair<long long, double>> acc;
+  std::vector<bbt::prof::ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lock(bbt::prof::g_prof_mu);
+    recs.swap(bbt::prof::g_prof_recs);
+  }
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      auto& a = acc[r.name];
+      a.first += 1;
+      a.second += ms;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto& kv : acc) {
+    char line[256];
+    snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    text += line;
+  }
+#endif
+  if ((int64_t)text.size() + 1 > size) return fail(BBT_EINVAL, "buffer too small");
+  memcpy(buf, text.c_str(), text.size() + 1);
+  return BBT_OK;
+}
 
 const char* bbt_last_error(void) { return g_err.c_str(); }
 
@@ -423,6 +517,7 @@ int launch_dd_col(bool inverse, const DdArgs& a, int64_t n_frames,
   auto kern = inverse ? dd_col_inv_kernel<L1> : dd_col_fwd_kernel<L1>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = inverse ? "dd_col_inv" : "dd_col_fwd";
   BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
   return check_launch("dedispersion column kernel");
 }
@@ -436,6 +531,7 @@ int launch_dd_row(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
   auto kern = dd_row_kernel<L2>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "dd_row";
   BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
   return check_launch("dedispersion row kernel");
 }
@@ -448,6 +544,7 @@ int launch_dd_small(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
   auto kern = dd_small_kernel<L, LANEFAST>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "dd_small";
   BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a,
              (long long)n_frames);
   return check_launch("dedispersion kernel");
@@ -558,6 +655,7 @@ int launch_chanpow(const ChanPowArgs& a, int64_t n_bins, bbt_stream_t st) {
   auto kern = chanpow_kernel<L, LANEFAST, INTEGRATE>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = INTEGRATE ? "chanpow_integrate" : "chanpow";
   BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
   return check_launch("channelize-power kernel");
 }
@@ -653,7 +751,7 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
                   int64_t i_first, const int64_t* lo, const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,
-                  const double* coef, int ncoef, int64_t i_ref, double rate,
+                  const double* coef, int ncoef, double i_ref, double rate,
                   int n_phase, void* sum, void* count, void* stream) {
   if (!in || !sum || !count || !lo || !hi) return fail(BBT_EINVAL, "null argument");
   if (!pbin && (!coef || ncoef < 1 || ncoef > 8))
@@ -691,6 +789,17 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
     BBT_LAUNCH(fold_kernel<false>, grid, dim3(256), a.use_smem ? smem : 0,
                as_stream(stream), a);
   return check_launch("fold kernel");
+}
+
+int bbt_average_exec(const void* sum, const void* count, void* out,
+                     int64_t n_bins, int64_t inner, void* stream) {
+  if (!sum || !count || !out) return fail(BBT_EINVAL, "null argument");
+  if (n_bins <= 0 || inner <= 0) return BBT_OK;
+  BBT_LAUNCH(average_kernel, dim3(grid_for(n_bins * inner, 256)), dim3(256), 0,
+             as_stream(stream), static_cast<const float*>(sum),
+             static_cast<const unsigned long long*>(count),
+             static_cast<float*>(out), (long long)n_bins, (long long)inner);
+  return check_launch("average kernel");
 }
 
 // ------------------------------------------------------- measurement helper

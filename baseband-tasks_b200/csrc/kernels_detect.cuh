@@ -196,7 +196,7 @@ BBT_GLOBAL void integrate_kernel(IntegrateArgs a) {
 // Fold: for every sample i of time bin b, phase bin
 //   p = int(((phase(i) mod 1) * n_phase))        (integration.py:389-391)
 // and sum[b][p][c] += x[i][c], count[b][p] += 1  (integration.py:394-395).
-// phase(i) = Horner(coef, dt), dt = (i_abs - i_ref) / rate, all in float64
+// phase(i) = Horner(coef, dt), dt = (double(i_abs) - i_ref) / rate, all in float64
 // with individually rounded operations (no FMA), so that the bin assignment
 // is bit-identical to the oracle's numpy arithmetic.  Alternatively the phase
 // bins may be supplied precomputed (pbin != nullptr) for arbitrary callables.
@@ -212,7 +212,7 @@ struct FoldArgs {
   long long inner;            // floats per sample in the output
   long long n, i_first;       // samples in this call; absolute index of first
   long long b_first;          // time bin of blockIdx.y = 0
-  long long i_ref;            // sample index at which dt = 0
+  double i_ref;               // sample index (may be fractional) at which dt = 0
   double rate;
   double coef[8];
   int ncoef;
@@ -221,7 +221,7 @@ struct FoldArgs {
 };
 
 BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
-  const double dt = ddiv((double)(i_abs - a.i_ref), a.rate);
+  const double dt = ddiv(dadd((double)i_abs, -a.i_ref), a.rate);
   double ph = a.coef[a.ncoef - 1];
   for (int k = a.ncoef - 2; k >= 0; --k) ph = dadd(dmul(ph, dt), a.coef[k]);
   double r = fmod(ph, 1.0);
@@ -285,6 +285,17 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
     for (int q = threadIdx.x; q < a.n_phase; q += blockDim.x)
       if (hcnt[q]) atomic_add(gcnt + q, (unsigned long long)hcnt[q]);
   }
+}
+
+// out[b][c] = sum[b][c] / count[b]; 0/0 gives NaN like numpy's division.
+BBT_GLOBAL void average_kernel(const float* BBT_RESTRICT sum,
+                               const unsigned long long* BBT_RESTRICT count,
+                               float* BBT_RESTRICT out, long long n_bins,
+                               long long inner) {
+  const long long total = n_bins * inner;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = sum[i] / (float)count[i / inner];
 }
 
 }  // namespace bbt

@@ -34,11 +34,16 @@ void bbt_emu_launch(dim3 grid, dim3 block, size_t smem,
 #define BBT_LAUNCH_BOUNDS(t, b)
 #define BBT_SMEM(type) reinterpret_cast<type*>(bbt_emu_smem())
 #define BBT_RESTRICT __restrict__
-#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  bbt_emu_launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
+#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+  do {                                                                \
+    bbt::prof_count();                                                \
+    bbt_emu_launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); }); \
+  } while (0)
 #define BBT_SET_SMEM(kernel, bytes) 0
 typedef void* bbt_stream_t;
 namespace bbt {
+void prof_count();
+extern thread_local const char* prof_next_name;
 inline float atomic_add(float* p, float v) {
   uint32_t* ip = reinterpret_cast<uint32_t*>(p);
   uint32_t old = __atomic_load_n(ip, __ATOMIC_RELAXED), nw;
@@ -86,8 +91,13 @@ inline int sm_count() { return 4; }
 #define BBT_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define BBT_SMEM(type) reinterpret_cast<type*>(bbt_dyn_smem)
 #define BBT_RESTRICT __restrict__
-#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// Every launch is counted; with profiling on (bbt_profile_enable) it is also
+// bracketed by CUDA events on its own stream.
+#define BBT_LAUNCH(kernel, grid, block, smem, stream, ...)   \
+  do {                                                       \
+    bbt::ProfScope bbt_prof_scope(#kernel, stream);          \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);      \
+  } while (0)
 #define BBT_SET_SMEM(kernel, bytes)                                         \
   ((bytes) > 48 * 1024                                                      \
        ? (int)cudaFuncSetAttribute(                                         \
@@ -96,6 +106,19 @@ inline int sm_count() { return 4; }
 typedef cudaStream_t bbt_stream_t;
 extern __shared__ float4 bbt_dyn_smem[];
 namespace bbt {
+void prof_count();
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end();
+// Name used for the next launch instead of the stringified kernel symbol.
+extern thread_local const char* prof_next_name;
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t stream) {
+    prof_count();
+    prof_begin(prof_next_name ? prof_next_name : name, stream);
+    prof_next_name = nullptr;
+  }
+  ~ProfScope() { prof_end(); }
+};
 __device__ __forceinline__ float atomic_add(float* p, float v) {
   return atomicAdd(p, v);
 }

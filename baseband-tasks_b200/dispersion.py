@@ -1,0 +1,261 @@
+"""Coherent (de)dispersion on the GPU.
+
+Mirrors `Disperse` / `Dedisperse` of the reference (dispersion.py:16-190):
+same arguments, padding from the band-edge delays (:54-93), start-time shift
+(:96), FFT length from the maker's ``next_fast_len`` (:97-101) and the same
+per-frame result ``ifft(fft(x) * phase_factor)[pad_start:pad_start+spf]``
+(:135-139).  The three numpy passes of the reference are one plan in the CUDA
+library (include/bbt_b200.h, bbt_dedisperse_*): the chirp is generated on the
+device in float64 and multiplied inside the middle FFT pass, whole runs of
+overlap-save frames are processed per launch, and only the valid samples of
+each frame are written.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _buffers as B
+from . import _cabi
+from ._units import to_float, to_mhz
+from .base import PaddedTaskBase, getattr_if_none
+from .dm import DispersionMeasure
+from .fourier import fft_maker
+from .fourier.cuda import CudaFFTMaker
+
+__all__ = ['Disperse', 'Dedisperse']
+
+
+class Disperse(PaddedTaskBase):
+    """Coherently disperse a time stream.
+
+    Parameters
+    ----------
+    ih : task or stream reader
+        Input data stream, with time as the first axis.
+    dm : float or `~baseband_tasks_b200.dm.DispersionMeasure`
+        Dispersion measure (pc/cm^3).  If negative, will dedisperse.
+    reference_frequency : frequency, optional
+        Frequency to which the data should be dispersed.  Can be an array.
+        By default, the mean frequency.
+    samples_per_frame : int, optional
+        Number of dispersed samples which should be produced in one go.  The
+        number of input samples used will be larger to avoid wrapping.  If
+        not given, the minimum power-of-two frame that gives at least 75%
+        efficiency.
+    frequency, sideband : optional
+        Frequencies and sidebands of the channels of ``ih``.  Default: taken
+        from ``ih``.
+    """
+    _on_device = True
+    _multi_frame = True
+
+    def __init__(self, ih, dm, *, reference_frequency=None,
+                 samples_per_frame=None, frequency=None, sideband=None):
+        dm = DispersionMeasure(dm)
+        frequency = getattr_if_none(ih, 'frequency', frequency)
+        sideband = getattr_if_none(ih, 'sideband', sideband)
+        sideband = np.where(np.asanyarray(sideband) > 0, 1, -1)
+        # Work in MHz and microseconds, like the oracle.
+        freq_mhz = to_mhz(frequency)
+        rate_mhz = to_mhz(ih.sample_rate)
+        half_rate = rate_mhz / 2.
+        if ih.complex_data:
+            freq_low = freq_mhz - half_rate
+            freq_high = freq_mhz + half_rate
+        else:
+            freq_low = freq_mhz + np.minimum(sideband, 0.) * half_rate
+            freq_high = freq_mhz + np.maximum(sideband, 0.) * half_rate
+
+        if reference_frequency is None:
+            fref_mhz = np.mean(freq_low + freq_high) / 2.
+            reference_frequency = fref_mhz * 1e6 * _unit_of(frequency)
+        else:
+            fref_mhz = to_mhz(reference_frequency)
+
+        delay_low = _time_delay(dm, freq_low, fref_mhz)
+        delay_high = _time_delay(dm, freq_high, fref_mhz)
+        delay_max = max(np.max(delay_low), np.max(delay_high))
+        delay_min = min(np.min(delay_low), np.min(delay_high))
+        rate_hz = rate_mhz * 1e6
+        pad_start = int(np.ceil(delay_max * rate_hz))
+        pad_end = int(np.ceil(-delay_min * rate_hz))
+        if pad_start < 0:
+            # Both delays less than 0: shift, and pad less at the end.
+            assert pad_end > 0
+            sample_offset = pad_start
+            pad_end += pad_start
+            pad_start = 0
+        elif pad_end < 0:
+            sample_offset = -pad_end
+            pad_start += pad_end
+            pad_end = 0
+        else:
+            sample_offset = 0
+
+        FFT = fft_maker.get()
+        if not isinstance(FFT, CudaFFTMaker):
+            raise TypeError("coherent dedispersion on the GPU needs the "
+                            "'cuda' FFT maker (fft_maker.set('cuda')).")
+        start_time = ih.start_time + sample_offset / ih.sample_rate
+        super().__init__(ih, pad_start=pad_start, pad_end=pad_end,
+                         samples_per_frame=samples_per_frame,
+                         next_fast_len=FFT.next_fast_len,
+                         frequency=frequency, sideband=sideband,
+                         start_time=start_time)
+        if not self.ih.complex_data:
+            raise NotImplementedError(
+                "coherent dedispersion of real-valued streams is not "
+                "implemented on the GPU; convert to complex first.")
+        self._FFT = FFT
+        self._dm = dm
+        self.reference_frequency = reference_frequency
+        self._sample_offset = sample_offset
+        self._pad_slice = slice(self._pad_start,
+                                self._pad_start + self.samples_per_frame)
+        self._rate_mhz = rate_mhz
+        # One chirp per distinct (frequency, reference, sideband).
+        shape = self.ih.sample_shape
+        f = np.broadcast_to(freq_mhz, shape).ravel()
+        r = np.broadcast_to(fref_mhz, shape).ravel()
+        s = np.broadcast_to(sideband, shape).ravel()
+        keys = list(zip(f.tolist(), r.tolist(), s.tolist()))
+        uniq = sorted(set(keys))
+        index = {k: i for i, k in enumerate(uniq)}
+        self._series_map = np.array([index[k] for k in keys], np.int32)
+        self._chirp_par = (np.array([u[0] for u in uniq], np.float64),
+                           np.array([u[1] for u in uniq], np.float64),
+                           np.array([u[2] for u in uniq], np.int8))
+        self._n_series = len(keys)
+        self._plan = None
+        self._work = None
+
+    # ------------------------------------------------------------- the plan
+    def _get_plan(self):
+        if self._plan is None:
+            lib = _cabi.lib()
+            f, r, s = self._chirp_par
+            plan = ctypes.c_void_p()
+            lib.check(lib.bbt_dedisperse_plan_create(
+                ctypes.byref(plan), self._ih_samples_per_frame,
+                self._n_series, self._pad_start, self.samples_per_frame,
+                len(f),
+                self._series_map.ctypes.data_as(
+                    ctypes.POINTER(ctypes.c_int32)),
+                f.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                r.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                s.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                float(self._dm), float(self._rate_mhz),
+                float(self._sample_offset), 0))
+            self._plan = plan
+        return self._plan
+
+    @property
+    def _fft(self):
+        """Forward transform of one frame (dispersion.py:105-107)."""
+        return self._FFT(shape=(self._ih_samples_per_frame,)
+                         + self.ih.sample_shape, dtype=self.ih.dtype,
+                         sample_rate=self.ih.sample_rate)
+
+    @property
+    def _ifft(self):
+        return self._fft.inverse()
+
+    @property
+    def phase_factor(self):
+        """Phase factors of the Fourier-transformed frame, as used by the
+        kernels: float64 phases rounded to complex64 (dispersion.py:115-129),
+        shape ``(N,) + sample_shape``."""
+        lib = _cabi.lib()
+        n = self._ih_samples_per_frame
+        host = np.empty((len(self._chirp_par[0]), n), np.complex64)
+        lib.check(lib.bbt_dedisperse_plan_get_response(
+            self._get_plan(), host.ctypes.data_as(ctypes.c_void_p)))
+        return host[self._series_map].T.reshape(
+            (n,) + self.ih.sample_shape)
+
+    @property
+    def dm(self):
+        return self._dm
+
+    # ------------------------------------------------------------ the work
+    def task_frames(self, data, n_frames, out=None):
+        """(De)disperse ``n_frames`` overlapping frames of a run of input.
+
+        ``data`` holds ``(n_frames-1)*samples_per_frame + N`` samples; frame i
+        starts at ``i*samples_per_frame``.  Returns (or fills ``out`` with)
+        the ``n_frames*samples_per_frame`` valid output samples.
+        """
+        lib = _cabi.lib()
+        plan = self._get_plan()
+        host = not B.is_tensor(data)
+        x = B.as_device(data, dtype=np.complex64)
+        S, spf = self._n_series, self.samples_per_frame
+        N = self._ih_samples_per_frame
+        assert x.shape[0] == (n_frames - 1) * spf + N
+        result = out
+        if result is None:
+            result = B.empty((n_frames * spf,) + self.sample_shape,
+                             np.complex64)
+        assert result.is_contiguous() and result.shape[0] == n_frames * spf
+        wb = lib.bbt_dedisperse_work_bytes(plan, n_frames)
+        if self._work is None or self._work.numel() < wb:
+            self._work = None
+            self._work = B.empty((max(wb, 16),), np.uint8)
+        lib.check(lib.bbt_dedisperse_exec(
+            plan, B.ptr(x), spf * S, n_frames, 0, B.ptr(result), spf * S,
+            B.ptr(self._work), _cabi.stream_ptr()))
+        if out is None and host:
+            return B.as_host(result)
+        return result
+
+    def task(self, data, out=None):
+        """One frame: N input samples to ``samples_per_frame`` outputs."""
+        return self.task_frames(data, 1, out=out)
+
+    def close(self):
+        super().close()
+        plan, self._plan = self._plan, None
+        self._work = None
+        if plan is not None:
+            _cabi.lib().bbt_dedisperse_plan_destroy(plan)
+
+    def __del__(self):
+        plan, self._plan = getattr(self, '_plan', None), None
+        if plan is not None:
+            try:
+                _cabi.lib().bbt_dedisperse_plan_destroy(plan)
+            except Exception:
+                pass
+
+
+class Dedisperse(Disperse):
+    """Coherently dedisperse a time stream (dispersion.py:149-190).
+
+    Parameters are as for `Disperse`; the dispersion measure is removed
+    rather than added.
+    """
+
+    def __init__(self, ih, dm, *, reference_frequency=None,
+                 samples_per_frame=None, frequency=None, sideband=None):
+        super().__init__(ih, -DispersionMeasure(dm),
+                         reference_frequency=reference_frequency,
+                         samples_per_frame=samples_per_frame,
+                         frequency=frequency, sideband=sideband)
+
+    @property
+    def dm(self):
+        return -self._dm
+
+
+def _time_delay(dm, f_mhz, fref_mhz):
+    d = DispersionMeasure.dispersion_delay_constant * float(dm)
+    return d * (1. / np.asarray(f_mhz)**2 - 1. / np.asarray(fref_mhz)**2)
+
+
+def _unit_of(quantity):
+    """1 Hz in the kind of object ``quantity`` is (Quantity or number)."""
+    unit = getattr(quantity, 'unit', None)
+    if unit is None:
+        return 1.
+    import astropy.units as u
+    return u.Hz

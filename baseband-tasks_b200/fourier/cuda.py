@@ -1,0 +1,153 @@
+"""The 'cuda' FFT maker: hand-written sm_100a Stockham kernels via the C ABI.
+
+Registered as ``'cuda'`` through `FFTMakerMeta`, exactly as the reference's
+makers register themselves (fourier/base.py:235-253), and selectable with
+``fft_maker.set('cuda')``.  Replaces `NumpyFFTBase` (fourier/numpy.py:13-49):
+unnormalised forward transform, 1/n on the inverse, 1/sqrt(n) both ways with
+``ortho`` (fourier/base.py:95-104); real transforms keep n//2+1 bins.
+
+Deliberate limits (no CPU fallback): lengths must be powers of two --
+``next_fast_len`` rounds up so padded tasks choose such lengths themselves
+(dispersion.py:99, base.py:757-758) -- and arithmetic is single precision
+(double-precision input is converted, with a warning).
+"""
+import ctypes
+import math
+import warnings
+
+import numpy as np
+
+from .. import _buffers as B
+from .. import _cabi
+from .base import FFTBase, FFTMakerBase
+
+__all__ = ['CudaFFTBase', 'CudaFFTMaker']
+
+_SINGLE = {'f': np.dtype('f4'), 'c': np.dtype('c8')}
+
+
+class CudaFFTBase(FFTBase):
+    """Single pre-defined FFT running on the GPU.
+
+    Accepts device tensors (returns a device tensor, data stay in HBM) or
+    numpy arrays (uploaded, transformed, downloaded).
+    """
+
+    def __init__(self, direction='forward'):
+        super().__init__(direction=direction)
+        self._plan = None
+        shape, axis = self._time_shape, self._axis % len(self._time_shape)
+        self._n = shape[axis]
+        self._outer = int(np.prod(shape[:axis], dtype=np.int64))
+        self._inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        real = self._time_dtype.kind == 'f'
+        forward = self.direction == 'forward'
+        if real:
+            self._kind = _cabi.BBT_R2C if forward else _cabi.BBT_C2R
+        else:
+            self._kind = _cabi.BBT_C2C
+        if self._ortho:
+            self._scale = 1. / math.sqrt(self._n)
+        else:
+            self._scale = 1. if forward else 1. / self._n
+        if forward:
+            self._in_shape, self._in_dtype = self._time_shape, self._time_dtype
+            self._out_shape, self._out_dtype = (self._frequency_shape,
+                                                self._frequency_dtype)
+        else:
+            self._in_shape, self._in_dtype = (self._frequency_shape,
+                                              self._frequency_dtype)
+            self._out_shape, self._out_dtype = (self._time_shape,
+                                                self._time_dtype)
+        # Lengths above the single-pass limit run on a contiguous axis.
+        self._transpose = self._n > 8192 and self._inner > 1
+
+    def _get_plan(self):
+        if self._plan is None:
+            lib = _cabi.lib()
+            plan = ctypes.c_void_p()
+            outer, inner = self._outer, self._inner
+            if self._transpose:
+                outer, inner = outer * inner, 1
+            lib.check(lib.bbt_fft_plan_create(
+                ctypes.byref(plan), self._n, outer, inner, self._kind,
+                _cabi.BBT_BACKWARD if self.direction == 'backward'
+                else _cabi.BBT_FORWARD, self._scale))
+            self._plan = plan
+            self._work_bytes = lib.bbt_fft_plan_work_bytes(plan)
+        return self._plan
+
+    def __call__(self, a, out=None):
+        """Transform ``a``; ``out`` may name a device tensor to fill."""
+        return self._fft(a, out=out)
+
+    def _fft(self, a, out=None):
+        host = not B.is_tensor(a)
+        if tuple(a.shape) != tuple(self._in_shape):
+            raise ValueError(f"input has shape {tuple(a.shape)}, transform "
+                             f"was set up for {tuple(self._in_shape)}.")
+        single_in = _SINGLE[self._in_dtype.kind]
+        single_out = _SINGLE[self._out_dtype.kind]
+        if self._in_dtype != single_in:
+            warnings.warn("the cuda FFT maker computes in single precision; "
+                          f"{self._in_dtype} data are converted.",
+                          stacklevel=3)
+        x = B.as_device(a, dtype=single_in)
+        lib = _cabi.lib()
+        plan = self._get_plan()
+        if self._transpose:
+            axis = self._axis % len(self._in_shape)
+            x = x.movedim(axis, -1).contiguous()
+            out = B.empty(x.shape, single_out)
+        elif (out is not None and out.is_contiguous()
+              and out.dtype == B.torch_dtype(single_out)
+              and out.numel() == int(np.prod(self._out_shape, dtype=np.int64))):
+            lib.check(lib.bbt_fft_exec(
+                plan, B.ptr(x), B.ptr(out),
+                B.ptr(B.empty((self._work_bytes,), np.uint8)
+                      if self._work_bytes else None), _cabi.stream_ptr()))
+            return out
+        else:
+            out = B.empty(self._out_shape, single_out)
+        work = (B.empty((self._work_bytes,), np.uint8)
+                if self._work_bytes else None)
+        lib.check(lib.bbt_fft_exec(plan, B.ptr(x), B.ptr(out), B.ptr(work),
+                                   _cabi.stream_ptr()))
+        if self._transpose:
+            out = out.movedim(-1, axis).contiguous()
+        if self._out_dtype != single_out:
+            out = out.to(B.torch_dtype(self._out_dtype))
+        return B.as_host(out) if host else out
+
+    def __del__(self):
+        plan, self._plan = getattr(self, '_plan', None), None
+        if plan is not None:
+            try:
+                _cabi.lib().bbt_fft_plan_destroy(plan)
+            except Exception:
+                pass
+
+
+class CudaFFTMaker(FFTMakerBase):
+    """FFT factory for the hand-written CUDA kernels (key ``'cuda'``)."""
+    _FFTBase = CudaFFTBase
+
+    def __call__(self, shape, dtype, direction='forward', axis=0, ortho=False,
+                 sample_rate=None):
+        n = tuple(shape)[axis]
+        if n < 2 or n & (n - 1):
+            raise NotImplementedError(
+                f"the cuda FFT maker needs power-of-two lengths, got {n}; "
+                "use CudaFFTMaker.next_fast_len to choose frame sizes.")
+        if n > 8192 and np.dtype(dtype).kind == 'f':
+            raise NotImplementedError(
+                "real transforms above 8192 points are not implemented.")
+        return super().__call__(shape=shape, dtype=dtype, direction=direction,
+                                axis=axis, ortho=ortho,
+                                sample_rate=sample_rate)
+
+    @staticmethod
+    def next_fast_len(n):
+        """Smallest power of two >= n (the lengths the kernels handle)."""
+        n = int(n)
+        return 1 if n <= 1 else 1 << (n - 1).bit_length()

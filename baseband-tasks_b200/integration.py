@@ -1,0 +1,468 @@
+"""Integration over time and folding on pulse phase, on the GPU.
+
+Mirrors `Integrate` and `Fold` of the reference (integration.py:52-395): same
+arguments and bin bookkeeping -- the bin edges in the upstream stream are
+``around(k / mean_offset_size + ih_start)`` (:184-186) computed on the host in
+float64 and handed to the kernels as one int64 table, so counts and bin
+assignment are bit-exact; empty bins average to NaN (:268-269);
+``average=False`` gives a structured array with ``data`` and ``count``.
+
+The segmented sums (:290-303) and the phase-bin scatter-add (:380-395) are CUDA
+kernels (bbt_integrate_exec, bbt_fold_exec).  When the input is
+``Power(Channelize(x))`` (or ``Power(x)`` for `Fold`) with the polarization
+axis last, the fused kernels read ``x`` directly, so detected spectra are
+never written to HBM.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _buffers as B
+from . import _cabi
+from . import base as _base
+from ._units import is_index, to_float
+from .base import BaseTaskBase
+from .channelize import Channelize
+from .functions import Power
+
+__all__ = ['Integrate', 'Fold', 'PolynomialPhase']
+
+_MAX_BINS_PER_LAUNCH = 32768
+
+
+class PolynomialPhase:
+    """Pulse phase as a polynomial in time, evaluable on the device.
+
+    ``phase(t) = sum_k coef[k] * dt**k`` cycles, with ``dt`` the time in
+    seconds since ``reference_time``.  As a ``phase`` callable it takes times
+    (like any other callable passed to `Fold`); `Fold` recognises it and
+    evaluates it inside the fold kernel from the sample index instead, as
+    ``dt = (float64(i) - i_ref) / sample_rate`` with Horner's rule and
+    individually rounded float64 operations -- `of_index` is the same
+    arithmetic in numpy (the documented time convention for bit-exact bins).
+    """
+
+    def __init__(self, coef, reference_time):
+        self.coef = np.atleast_1d(np.asarray(coef, dtype=np.float64))
+        if not 1 <= len(self.coef) <= 8:
+            raise ValueError("need between 1 and 8 coefficients.")
+        self.reference_time = reference_time
+
+    def __call__(self, time):
+        dt = np.asarray(to_float(time - self.reference_time),
+                        dtype=np.float64)
+        return self._horner(dt)
+
+    def _horner(self, dt):
+        phase = np.full(np.shape(dt), self.coef[-1])
+        for c in self.coef[-2::-1]:
+            phase = phase * dt + c
+        return phase
+
+    def i_ref(self, start_time, sample_rate):
+        """Stream sample index (fractional) at which ``dt`` is zero."""
+        return float(to_float((self.reference_time - start_time)
+                              * sample_rate))
+
+    def of_index(self, index, i_ref, sample_rate):
+        rate = float(to_float(sample_rate * 1.))
+        dt = (np.asarray(index).astype(np.float64) - i_ref) / rate
+        return self._horner(dt)
+
+
+class Integrate(BaseTaskBase):
+    """Integrate a stream stepwise.
+
+    Parameters
+    ----------
+    ih : task or stream reader
+        Input data stream, with time as the first axis.
+    step : int or time interval, optional
+        Interval over which to integrate: a number of samples of the
+        underlying stream, a time (seconds or a quantity), or, with ``phase``,
+        a phase interval.  Default: all samples.
+    phase : callable, optional
+        Should return full pulse phase (including cycle count) for the times
+        passed in; integration is then over intervals of ``step`` in phase.
+    start : time or int, optional
+        Time or offset at which to start the integration.  Default: 0.
+    average : bool, optional
+        Whether to return the average (default) or, in a structured array
+        with ``'data'`` and ``'count'``, the sums and numbers of samples.
+    samples_per_frame : int, optional
+        Number of output samples per frame.  Default: 1.  (Reads of many
+        samples are integrated in one pass whatever this is.)
+    dtype : `~numpy.dtype`, optional
+        Output dtype.
+    """
+    _on_device = True
+
+    def __init__(self, ih, step=None, phase=None, *,
+                 start=0, average=True, samples_per_frame=1, dtype=None):
+        self._start = start
+        self._step = step
+
+        ih_start = ih.seek(start)
+        ih_n_sample = ih.shape[0] - ih_start
+        if ih_start < 0 or ih_n_sample < 0:
+            raise ValueError("'start' is not within the underlying stream.")
+
+        if not is_index(start):
+            # A time: we may not be at an integer sample.
+            ih_start += to_float((start - ih.time) * ih.sample_rate)
+        else:
+            start = ih.time
+
+        if step is None:
+            step = ih_n_sample
+
+        if is_index(step):
+            assert phase is None, 'cannot pass in phase and integer step'
+            sample_rate = ih.sample_rate / step
+            n_sample = ih_n_sample / step
+        else:
+            stop = ih.stop_time
+            if phase is not None:
+                start = phase(start)
+                stop = phase(stop)
+            sample_rate = 1 / step
+            n_sample = to_float((stop - start) * sample_rate)
+
+        self._mean_offset_size = n_sample / ih_n_sample
+        self._sample_start = start
+
+        n_sample = int(n_sample + 0.5 * self._mean_offset_size)
+        assert n_sample >= 1, "time per frame larger than total time in stream"
+        shape = (n_sample,) + tuple(ih.sample_shape)
+        # Without a phase the start is a time and the rate a frequency.
+        start_time = start if phase is None else False
+
+        if dtype is None:
+            if average:
+                dtype = ih.dtype
+            else:
+                dtype = np.dtype([('data', ih.dtype), ('count', int)])
+
+        super().__init__(ih, shape=shape, sample_rate=sample_rate,
+                         samples_per_frame=samples_per_frame,
+                         start_time=start_time, dtype=dtype)
+        self.average = average
+        self._phase = phase
+        self._ih_start = ih_start
+        self._setup_source()
+
+    # ------------------------------------------------------------- sources
+    def _setup_source(self):
+        """Decide what the kernels read: ``ih`` itself or, fused, the input
+        of ``Power(Channelize(x))``."""
+        ih = self.ih
+        self._fused = None
+        self._src = ih
+        self._src_ratio = 1      # source samples per ih sample
+        if (type(ih) is Power and type(getattr(ih, 'ih', None)) is Channelize
+                and np.dtype(ih.ih.ih.dtype) == np.complex64
+                and ih._axis == ih.ndim - 1 and ih.ih.ih.ndim >= 2):
+            ch = ih.ih
+            self._fused = 'chanpow'
+            self._src = ch.ih
+            self._src_ratio = ch._n
+            self._chan_n = ch._n
+            self._chan_m = int(np.prod(ch.ih.sample_shape[:-1],
+                                       dtype=np.int64))
+
+    def _tell_time(self, offset):
+        if self._start_time is not False:
+            return super()._tell_time(offset)
+        return self.ih._tell_time(self._get_offsets(offset))
+
+    def _get_offsets(self, samples, precision=1.e-3, max_iter=10):
+        """Offsets in the underlying stream nearest to the given output
+        sample edges (integration.py:174-228)."""
+        if self._phase is None:
+            return (np.around(np.asanyarray(samples) / self._mean_offset_size
+                              + self._ih_start).astype(int))
+
+        # Requested phases relative to the start.
+        phase = to_float(np.ravel(samples) / self.sample_rate)
+        ih_mean_phase_size = to_float(self._mean_offset_size
+                                      / self.sample_rate)
+        offsets = phase / ih_mean_phase_size
+        all_offsets = np.hstack((0, offsets,
+                                 self.ih.shape[0] - self._ih_start))
+        all_ih_phase = all_offsets * ih_mean_phase_size
+        all_offsets += self._ih_start
+        offsets = all_offsets[1:-1]
+        ih_phase = all_ih_phase[1:-1]
+        mask = np.ones(offsets.shape, bool)
+        it = 0
+        while np.any(mask) and it < max_iter:
+            old_offsets = offsets[mask]
+            ih_time = self.ih.start_time + old_offsets / self.ih.sample_rate
+            ih_phase[mask] = np.asarray(to_float(
+                self._phase(ih_time) - self._sample_start), dtype=float)
+            offsets[mask] = np.interp(phase[mask], all_ih_phase, all_offsets)
+            mask[mask] = abs(offsets[mask] - old_offsets) > precision
+            it += 1
+
+        if it >= max_iter:  # pragma: no cover
+            warnings.warn('offset calculation did not converge. '
+                          'This should not happen!')
+
+        shape = getattr(samples, 'shape', ())
+        return offsets.round().astype(int).reshape(shape)
+
+    # -------------------------------------------------------------- reading
+    def _read_frame(self, frame_index):
+        sample0 = frame_index * self.samples_per_frame
+        n_sample = min(self.samples_per_frame, self.shape[0] - sample0)
+        return self._integrate_samples(sample0, n_sample)
+
+    def _read_data(self, count, out=None):
+        # Many output samples in one pass over the upstream data (results
+        # per bin do not depend on how output samples are grouped in frames).
+        if count == 0 or self._frame_dependent():
+            return super()._read_data(count, out)
+        per_sample = max(1, 4 * int(np.prod(self.sample_shape,
+                                            dtype=np.int64)))
+        max_n = max(1, _base.BLOCK_BYTES // per_sample)
+        a = self.offset
+        if count <= max_n and out is None:
+            result = self._integrate_samples(a, count)
+        else:
+            result = out
+            pos = 0
+            while pos < count:
+                n = min(max_n, count - pos)
+                part = self._integrate_samples(a + pos, n)
+                if result is None:
+                    result = _base._empty_like(
+                        part, (count,) + tuple(part.shape[1:]))
+                result[pos:pos + n] = part
+                pos += n
+        self.offset = a + count
+        return result
+
+    def _frame_dependent(self):
+        return False
+
+    def _integrate_samples(self, sample0, n_sample):
+        """Output samples [sample0, sample0 + n_sample)."""
+        samples = np.arange(sample0, sample0 + n_sample + 1)
+        offsets = self._get_offsets(samples).astype(np.int64)
+        inner = int(np.prod(self.ih.sample_shape, dtype=np.int64))
+        if self.ih.complex_data:
+            inner *= 2
+        sums = B.zeros((n_sample, inner), np.float32)
+        count = B.zeros((n_sample,), np.int64)
+        self._accumulate(offsets, sums, count)
+        return self._finish(sums, count, (n_sample,) + self.sample_shape)
+
+    def _finish(self, sums, count, shape):
+        """Average on the device, or assemble the structured host array."""
+        lib = _cabi.lib()
+        ih_dtype = np.dtype(self.ih.dtype)
+        single = np.complex64 if ih_dtype.kind == 'c' else np.float32
+        if self.average:
+            out = B.empty(sums.shape, np.float32)
+            lib.check(lib.bbt_average_exec(
+                B.ptr(sums), B.ptr(count), B.ptr(out), count.numel(),
+                sums.numel() // max(count.numel(), 1), _cabi.stream_ptr()))
+            out = _as_dtype(out, single).reshape(shape)
+            if self.dtype != np.dtype(single):
+                out = out.to(B.torch_dtype(self.dtype))
+            return out
+        data = B.as_host(_as_dtype(sums, single)).reshape(shape)
+        frame = np.zeros(shape, dtype=self.dtype)
+        frame['data'] = data
+        cnt = B.as_host(count)
+        frame['count'] = cnt.reshape(cnt.shape + (1,) * (
+            len(shape) - cnt.ndim))
+        return frame
+
+    def _accumulate(self, offsets, sums, count):
+        """Add upstream samples [offsets[0], offsets[-1]) to their bins."""
+        lib = _cabi.lib()
+        d_off = B.as_device(offsets)
+        n_bins = len(offsets) - 1
+        start, stop = int(offsets[0]), int(offsets[-1])
+        ratio = self._src_ratio
+        src = self._src
+        per_sample = (int(np.prod(src.sample_shape, dtype=np.int64))
+                      * np.dtype(src.dtype).itemsize * ratio)
+        chunk = max(1, _base.BLOCK_BYTES // max(per_sample, 1))
+        # Prefer chunks aligned with the frames of the source.
+        src_spf = max(1, getattr(src, 'samples_per_frame', 1) // ratio)
+        if chunk > src_spf:
+            chunk = (chunk // src_spf) * src_spf
+        pos = start
+        while pos < stop:
+            nxt = min(stop, (pos // chunk + 1) * chunk)
+            n = nxt - pos
+            src.seek(pos * ratio)
+            if hasattr(src, 'read_device'):
+                x = src.read_device(n * ratio)
+            else:
+                x = B.as_device(src.read(n * ratio))
+            # Bins with any overlap with [pos, nxt).
+            b0 = int(np.searchsorted(offsets[1:], pos, side='right'))
+            b1 = int(np.searchsorted(offsets[:-1], nxt, side='left'))
+            for bb in range(b0, b1, _MAX_BINS_PER_LAUNCH):
+                nb = min(_MAX_BINS_PER_LAUNCH, b1 - bb)
+                if self._fused == 'chanpow':
+                    lib.check(lib.bbt_channelize_power_integrate_exec(
+                        B.ptr(x), self._chan_n, self._chan_m, n, pos,
+                        B.ptr(d_off), bb, nb, B.ptr(sums), B.ptr(count),
+                        _cabi.stream_ptr()))
+                else:
+                    x = _as_float32(x, src.dtype)
+                    lib.check(lib.bbt_integrate_exec(
+                        B.ptr(x), n, sums.shape[1], pos, B.ptr(d_off), bb,
+                        nb, B.ptr(sums), B.ptr(count), _cabi.stream_ptr()))
+            pos = nxt
+        assert n_bins == count.shape[0]
+
+
+def _as_dtype(t, dtype):
+    """View float32 pairs as complex64 where the stream is complex."""
+    if np.dtype(dtype).kind == 'c':
+        return B.torch().view_as_complex(t.reshape(t.shape[:-1] + (-1, 2)))
+    return t
+
+
+def _as_float32(x, dtype):
+    dtype = np.dtype(dtype)
+    t = B.torch()
+    if dtype.kind == 'c':
+        if dtype != np.complex64:
+            x = x.to(t.complex64)
+        return t.view_as_real(x)
+    if dtype != np.float32:
+        x = x.to(t.float32)
+    return x
+
+
+class Fold(Integrate):
+    """Fold pulse profiles in fixed time intervals.
+
+    Parameters
+    ----------
+    ih : task or stream reader
+        Input data stream, with time as the first axis.
+    n_phase : int
+        Number of bins per pulse period.
+    phase : callable
+        Should return pulse phases (with or without cycle count, in cycles)
+        for the times passed in.  A `PolynomialPhase` is evaluated inside the
+        fold kernel; any other callable is evaluated on the host, per sample,
+        like the reference does.
+    step : int or time interval, optional
+        Number of input samples or time interval over which to fold.
+        Default: the whole stream, in a single profile.
+    start, average, samples_per_frame, dtype
+        As for `Integrate` (``dtype`` is ignored, as in the reference).
+    """
+
+    def __init__(self, ih, n_phase, phase, step=None, *,
+                 start=0, average=True, samples_per_frame=1, dtype=None):
+        super().__init__(ih, step=step, start=start, average=average,
+                         samples_per_frame=samples_per_frame)
+        self._shape = (self._shape[0], n_phase) + tuple(ih.sample_shape)
+        self.n_phase = n_phase
+        self.phase = phase
+
+    def _setup_source(self):
+        ih = self.ih
+        self._fused = None
+        self._src = ih
+        self._src_ratio = 1
+        if (type(ih) is Power and np.dtype(ih.ih.dtype) == np.complex64
+                and ih._axis == ih.ndim - 1):
+            self._fused = 'power'
+            self._src = ih.ih
+
+    def _frame_dependent(self):
+        # With several time bins per frame the reference assigns a sample
+        # exactly on an inner bin edge to the earlier bin (searchsorted
+        # side='left', integration.py:386): results depend on the framing.
+        return self.samples_per_frame > 1
+
+    def _integrate_samples(self, sample0, n_sample):
+        samples = np.arange(sample0, sample0 + n_sample + 1)
+        offsets = self._get_offsets(samples).astype(np.int64)
+        lo = offsets[:-1].copy()
+        hi = offsets[1:].copy()
+        if self.samples_per_frame > 1 and n_sample > 1:
+            lo[1:] += 1
+            hi[:-1] += 1
+        inner = int(np.prod(self.ih.sample_shape, dtype=np.int64))
+        if self.ih.complex_data:
+            inner *= 2
+        sums = B.zeros((n_sample, self.n_phase, inner), np.float32)
+        count = B.zeros((n_sample, self.n_phase), np.int64)
+        self._fold(offsets, lo, hi, inner, sums, count)
+        return self._finish(sums, count,
+                            (n_sample, self.n_phase) + self.sample_shape[1:])
+
+    def _fold(self, offsets, lo, hi, inner, sums, count):
+        lib = _cabi.lib()
+        d_lo, d_hi = B.as_device(lo), B.as_device(hi)
+        start, stop = int(offsets[0]), int(offsets[-1])
+        src = self._src
+        ih = self.ih
+        per_sample = (int(np.prod(src.sample_shape, dtype=np.int64))
+                      * np.dtype(src.dtype).itemsize)
+        chunk = max(1, _base.BLOCK_BYTES // max(per_sample, 1))
+        src_spf = max(1, getattr(src, 'samples_per_frame', 1))
+        if chunk > src_spf:
+            chunk = (chunk // src_spf) * src_spf
+        poly = self.phase if isinstance(self.phase, PolynomialPhase) else None
+        if poly is not None:
+            rate = float(to_float(ih.sample_rate * 1.))
+            i_ref = poly.i_ref(ih.start_time, ih.sample_rate)
+            coef = poly.coef
+            coef_p = coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        # Time of the first sample folded in this frame (integration.py:375).
+        ih.seek(start)
+        raw_time = ih.time
+        pos = start
+        while pos < stop:
+            nxt = min(stop, (pos // chunk + 1) * chunk)
+            n = nxt - pos
+            src.seek(pos)
+            if hasattr(src, 'read_device'):
+                x = src.read_device(n)
+            else:
+                x = B.as_device(src.read(n))
+            if self._fused is None:
+                x = _as_float32(x, src.dtype)
+            if poly is None:
+                raw_items = np.arange(pos - start, nxt - start)
+                phases = self.phase(raw_time + raw_items / ih.sample_rate)
+                phases = np.asarray(_cycles(phases), dtype=np.float64)
+                pbin = ((phases % 1.) * self.n_phase).astype(np.int32)
+                d_pbin = B.as_device(pbin)
+            b0 = int(np.searchsorted(hi, pos, side='right'))
+            b1 = int(np.searchsorted(lo, nxt, side='left'))
+            for bb in range(b0, b1, _MAX_BINS_PER_LAUNCH):
+                nb = min(_MAX_BINS_PER_LAUNCH, b1 - bb)
+                if poly is None:
+                    lib.check(lib.bbt_fold_exec(
+                        B.ptr(x), int(self._fused == 'power'), n, inner, pos,
+                        B.ptr(d_lo), B.ptr(d_hi), bb, nb, B.ptr(d_pbin),
+                        None, 0, 0., 1., self.n_phase, B.ptr(sums),
+                        B.ptr(count), _cabi.stream_ptr()))
+                else:
+                    lib.check(lib.bbt_fold_exec(
+                        B.ptr(x), int(self._fused == 'power'), n, inner, pos,
+                        B.ptr(d_lo), B.ptr(d_hi), bb, nb, None, coef_p,
+                        len(coef), i_ref, rate, self.n_phase, B.ptr(sums),
+                        B.ptr(count), _cabi.stream_ptr()))
+            pos = nxt
+
+
+def _cycles(phases):
+    """Phases as plain numbers of cycles (quantities are converted)."""
+    if hasattr(phases, 'to_value'):
+        return phases.to_value('cycle')
+    return phases

@@ -1,0 +1,460 @@
+"""Benchmark of the Dedisperse -> Channelize -> Power -> Integrate chain.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4]
+                    [--impl b200|reference]
+
+One step = one pass of the chain over one block of F overlap-save frames of
+a synthetic NoiseGenerator stream:
+
+  C2 (default; BASELINE.json configs[1]): (T, 8, 2) complex64, 8 channels of
+     8 MHz at 1372+8k MHz, Dedisperse(DM=100, N=2^20) -> Channelize(1024) ->
+     Power -> Integrate(1 ms).
+  C4 (configs[3], the north-star target): (T, 2) complex64, 512 MHz at
+     8192 MHz, Dedisperse(DM=1000, N=2^24) -> Channelize(1024) -> Power ->
+     Integrate(1 ms).
+
+``value``: complex source samples (time x channel x polarization) per second
+through the public Task API with the input block resident in HBM.  ``e2e``:
+the same with the block in pinned host memory, copied to the device inside
+the timed region, and the integrated spectra copied back.  Timing: CUDA
+events, max over ranks.  With N > 1 every rank processes its own time block
+of the stream (time-block sharding with an overlap-save halo; no collective
+on this chain), so scaling is weak.
+
+``--impl reference`` times the reference's CPU path -- its numpy arithmetic
+restated in oracle/bbt_oracle.py, since the reference itself needs astropy and
+baseband, which are not installable here -- on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # rate/Hz, channel frequencies/Hz, DM, log2 N, frames per step
+    'C2': dict(rate=8e6, freq=(1372e6 + 8e6 * np.arange(8)).reshape(8, 1),
+               sample_shape=(8, 2), dm=100., log2n=20, frames=8,
+               n_chan=1024, step=1e-3, seed=1234567 + 2,
+               desc='8ch x 2pol x 8 MHz c64 -> Dedisperse(DM=100, N=2^20) -> '
+                    'Channelize(1024) -> Power -> Integrate(1 ms)'),
+    'C4': dict(rate=512e6, freq=8192e6, sample_shape=(2,), dm=1000.,
+               log2n=24, frames=4, n_chan=1024, step=1e-3, seed=1234567 + 4,
+               desc='2pol x 512 MHz c64 -> Dedisperse(DM=1000, N=2^24) -> '
+                    'Channelize(1024) -> Power -> Integrate(1 ms)'),
+}
+
+
+def framing(w):
+    """Overlap-save framing, as Disperse.__init__ derives it
+    (reference dispersion.py:54-93), for samples_per_frame = N - pad."""
+    k = 1. / 2.41e-4
+    rate_mhz = w['rate'] / 1e6
+    f = np.asarray(w['freq'], float) / 1e6
+    lo, hi = f - rate_mhz / 2, f + rate_mhz / 2
+    fref = np.mean(lo + hi) / 2.
+    d = k * -w['dm']
+
+    def delay(x):
+        return d * (1. / x ** 2 - 1. / fref ** 2)
+    dmax = max(np.max(delay(lo)), np.max(delay(hi)))
+    dmin = min(np.min(delay(lo)), np.min(delay(hi)))
+    pad_start = int(np.ceil(dmax * w['rate']))
+    pad_end = int(np.ceil(-dmin * w['rate']))
+    N = 1 << w['log2n']
+    spf = N - pad_start - pad_end
+    return N, spf, pad_start, pad_end
+
+
+def model_bytes(w):
+    """Pre-registered algorithmic bytes per source sample."""
+    N, spf, _, _ = framing(w)
+    eff = spf / N
+    per_bin = w['step'] * w['rate'] / w['n_chan']
+    return 48. / eff + 8. + 8. / per_bin
+
+
+def clocks_sampler(device_index):
+    cmd = ['nvidia-smi', '-i', str(device_index),
+           '--query-gpu=clocks.sm,clocks.max.sm,'
+           'clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap',
+           '--format=csv,noheader,nounits', '-lms', '100']
+    try:
+        return subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return None
+
+
+def clocks_summary(proc):
+    if proc is None:
+        return None
+    proc.terminate()
+    try:
+        out, _ = proc.communicate(timeout=5)
+    except Exception:
+        proc.kill()
+        return None
+    sm, smax, reasons = [], 0., set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for line in out.strip().splitlines():
+        parts = [p.strip() for p in line.split(',')]
+        if len(parts) < 6:
+            continue
+        try:
+            sm.append(float(parts[0]))
+            smax = max(smax, float(parts[1]))
+        except ValueError:
+            continue
+        for name, val in zip(names, parts[2:6]):
+            if val.lower().startswith('active'):
+                reasons.add(name)
+    if not sm:
+        return None
+    return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': smax,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------- GPU arm
+def make_block(w, rank):
+    """One step's input: F frames of the NoiseGenerator stream (host)."""
+    import baseband_tasks_b200 as bt
+    N, spf, _, _ = framing(w)
+    n_in = (w['frames'] - 1) * spf + N
+    gen_spf = 1 << 20
+    # Rank r owns frames [r F, (r+1) F) of the stream: its block starts at
+    # r F spf (a halo of pad samples is shared with the next rank).
+    start = rank * w['frames'] * spf
+    total = start + n_in
+    total = -(-total // gen_spf) * gen_spf
+    nh = bt.NoiseGenerator((total,) + w['sample_shape'], bt.Time(1289567655),
+                           w['rate'], samples_per_frame=gen_spf,
+                           dtype='c8', seed=w['seed'])
+    nh.seek(start)
+    return nh.read(n_in), start
+
+
+def build_chain(w, data, start):
+    import baseband_tasks_b200 as bt
+    N, spf, _, _ = framing(w)
+    t0 = bt.Time(1289567655) + start / w['rate']
+    pol = np.array(['X', 'Y'])
+    src = bt.ArrayStream(data, t0, w['rate'], samples_per_frame=1 << 20,
+                         frequency=w['freq'], sideband=1, polarization=pol)
+    dd = bt.Dedisperse(src, w['dm'], samples_per_frame=spf)
+    assert dd._ih_samples_per_frame == N, (dd._ih_samples_per_frame, N)
+    ch = bt.Channelize(dd, w['n_chan'])
+    pw = bt.Power(ch)
+    it = bt.Integrate(pw, w['step'])
+    return src, it
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import baseband_tasks_b200 as bt
+    from baseband_tasks_b200 import _cabi
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    lib = _cabi.lib()
+    w = WORKLOADS[args.workload]
+    N, spf, pad_start, pad_end = framing(w)
+    S = int(np.prod(w['sample_shape']))
+
+    host_np, start = make_block(w, rank)
+    host = torch.from_numpy(host_np).pin_memory()
+    dev_in = host.to('cuda', non_blocking=True)
+    torch.cuda.synchronize()
+    samples_per_step = w['frames'] * spf * S
+
+    # HBM-resident chain.
+    src, chain = build_chain(w, dev_in, start)
+    out_host = None
+
+    def step_resident():
+        chain.seek(0)
+        return chain.read_device()
+
+    # End to end: pinned host block -> device -> chain -> host.
+    dev_stage = torch.empty_like(dev_in)
+    _, chain_e2e = build_chain(w, dev_stage, start)
+
+    def step_e2e():
+        nonlocal out_host
+        dev_stage.copy_(host, non_blocking=True)
+        chain_e2e.seek(0)
+        res = chain_e2e.read_device()
+        if out_host is None:
+            out_host = torch.empty(res.shape, dtype=res.dtype,
+                                   pin_memory=True)
+        out_host.copy_(res, non_blocking=True)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        res = step_resident()
+    out_bytes = res.numel() * res.element_size()
+    sampler = clocks_sampler(local) if rank == 0 else None
+    l0 = lib.bbt_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.bbt_launch_count() - l0
+    clocks = clocks_summary(sampler)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # Per-kernel durations, CUDA events on the launching stream.
+    lib.bbt_profile_enable(1)
+    barrier()
+    for _ in range(args.steps):
+        step_resident()
+    barrier()
+    lib.bbt_profile_enable(0)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.check(lib.bbt_profile_report(buf, len(buf)))
+    kernels = {}
+    for line in buf.value.decode().splitlines():
+        name, count, total = line.split()
+        kernels[name] = (int(count), float(total))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.))
+    peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+    # Dominant kernel and its algorithmic bytes per launch.
+    points = w['frames'] * N * S              # FFT points per dedisperse pass
+    alg = {'dd_col_fwd': 16. * points, 'dd_row': 16. * points,
+           'dd_col_inv': 8. * points + 8. * w['frames'] * spf * S,
+           'chanpow_integrate': 8. * samples_per_step + out_bytes}
+    top = max((k for k in kernels if k in alg),
+              key=lambda k: kernels[k][1], default=None)
+    roofline = None
+    if top:
+        count, total_ms = kernels[top]
+        per_launch_ms = total_ms / count
+        achieved = alg[top] / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+                traffic = json.load(f).get(args.workload, {}).get(top)
+        except OSError:
+            pass
+        roofline = {'bound': 'hbm', 'kernel': top, 'achieved': achieved,
+                    'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': traffic,
+                    'ms_per_launch': per_launch_ms,
+                    'algorithmic_bytes_per_launch': alg[top]}
+    total_kernel_ms = sum(v[1] for v in kernels.values()) or 1.
+    shares = {k: {'launches': v[0], 'ms_per_launch': v[1] / v[0],
+                  'share': v[1] / total_kernel_ms}
+              for k, v in sorted(kernels.items())}
+
+    value = samples_per_step * args.steps * world / (ms * 1e-3) / 1e9
+    e2e = samples_per_step * args.steps * world / (ms_e2e * 1e-3) / 1e9
+    mb = model_bytes(w)
+    cpu = cpu_baseline(w, budget_s=15.)
+    line = {
+        'metric': 'Dedisperse->Channelize->Power->Integrate complex '
+                  'Gsamples/s',
+        'value': value, 'unit': 'Gsamples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64 (fp32)',
+        'data': 'synthetic (NoiseGenerator, Philox)',
+        'config': {'workload': f"{args.workload}: {w['desc']}",
+                   'frames_per_step': w['frames'], 'fft_length': N,
+                   'samples_per_frame': spf, 'series': S,
+                   'input_bytes_per_step': int(host_np.nbytes),
+                   'l2': 'inputs (%.2f GB per step) larger than L2'
+                         % (host_np.nbytes / 1e9),
+                   'sharding': 'time blocks with overlap-save halo, one per '
+                               'rank; no collective'},
+        'e2e': {'value': e2e, 'unit': 'Gsamples/s',
+                'h2d_bytes_per_step': int(host_np.nbytes),
+                'd2h_bytes_per_step': int(out_bytes),
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': roofline,
+        'chain_roofline': {
+            'model_bytes_per_sample': mb,
+            'achieved_gbs': value * mb, 'peak': peak,
+            'frac': value * mb / peak, 'frac_of_8TBs_nominal':
+            value * mb / 8000.},
+        'kernels': shares,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- CPU arm
+def _cpu_unit(args):
+    """One (frame, channel) unit of the chain with the oracle (numpy)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import bbt_oracle as orc
+    wname, chan, seed = args
+    w = WORKLOADS[wname]
+    N, spf, pad_start, pad_end = framing(w)
+    rng = np.random.default_rng(seed)
+    npol = w['sample_shape'][-1]
+    x = (rng.normal(size=(N, npol)) + 1j * rng.normal(size=(N, npol))
+         ).astype('c8')
+    f = np.asarray(w['freq'], float).ravel() / 1e6
+    lo, hi = f - w['rate'] / 2e6, f + w['rate'] / 2e6
+    fref = np.mean(lo + hi) / 2.
+    plan = orc.DispersePlan(-w['dm'], f[chan % len(f)], 1, w['rate'] / 1e6,
+                            True, N, 1, (npol,), reference_frequency_mhz=fref,
+                            samples_per_frame=spf, fast_len=orc.next_pow2)
+    plan.pad_start, plan.pad_end = pad_start, pad_end
+    plan.samples_per_frame = spf
+    t0 = time.perf_counter()
+    pf = plan.phase_factor('c8')
+    t1 = time.perf_counter()
+    y = orc.disperse(x, plan, phase_factor=pf)
+    spectra = orc.channelize(y, w['n_chan'])
+    power = orc.power(spectra, axis=-1)
+    ip = orc.IntegratePlan(power.shape[0], w['rate'] / w['n_chan'],
+                           w['step'])
+    offsets = ip.offsets(np.arange(ip.n_out + 1))
+    orc.integrate(power, offsets)
+    t2 = time.perf_counter()
+    return spf * npol, t2 - t1, t1 - t0
+
+
+def cpu_run(w_name, cores, units):
+    """Process ``units`` (frame, channel) units on ``cores`` processes."""
+    import multiprocessing as mp
+    jobs = [(w_name, i, 100 + i) for i in range(units)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_unit(j) for j in jobs]
+    else:
+        with mp.get_context('fork').Pool(cores) as pool:
+            res = pool.map(_cpu_unit, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall, sum(r[1] for r in res)
+
+
+def cpu_baseline(w, budget_s=15.):
+    name = [k for k, v in WORKLOADS.items() if v is w][0]
+    # One unit first, to size the sample.
+    n, wall, busy = cpu_run(name, 1, 1)
+    units = int(max(1, min(16, budget_s / max(busy, 1e-3))))
+    if units > 1:
+        n2, wall2, busy2 = cpu_run(name, 1, units)
+        n, busy = n + n2, busy + busy2
+        units += 1
+    return {'value': n / busy / 1e9, 'unit': 'Gsamples/s', 'cores': 1,
+            'kind': 'port',
+            'sample': f'{units} (frame, channel) units of the same workload '
+                      '(one N-point frame of one channel, both '
+                      'polarizations) through oracle/bbt_oracle.py '
+                      '(numpy.fft); chirp construction excluded'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    w = WORKLOADS[args.workload]
+    cores = len(os.sched_getaffinity(0))
+    n_series_groups = max(1, int(np.prod(w['sample_shape'][:-1])))
+    units = max(cores, n_series_groups)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(args.workload, cores, units)
+    total, wall = 0, 0.
+    steps = args.steps
+    for _ in range(steps):
+        n, t, _ = cpu_run(args.workload, cores, units)
+        total += n
+        wall += t
+    value = total / wall / 1e9
+    N, spf, _, _ = framing(w)
+    sample = (f'{units} (frame, channel) units per step on {cores} processes '
+              '(numpy.fft restatement of the reference; the reference needs '
+              'astropy+baseband, not installable here)')
+    line = {
+        'impl': 'reference',
+        'metric': 'Dedisperse->Channelize->Power->Integrate complex '
+                  'Gsamples/s',
+        'value': value, 'unit': 'Gsamples/s', 'n_gpus': 0,
+        'steps': steps, 'warmup': min(args.warmup, 1),
+        'ms_per_step': wall / steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64 (fp32)',
+        'data': 'synthetic',
+        'config': {'workload': f"{args.workload}: {w['desc']}",
+                   'fft_length': N, 'samples_per_frame': spf},
+        'cpu_baseline': {'value': value, 'unit': 'Gsamples/s',
+                         'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'Gsamples/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -126,16 +126,31 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
  * covers absolute samples [lo[b], hi[b]) (device int64; the host applies the
  * reference's searchsorted convention).  Phase bins come either from pbin
  * (device int32 per sample of this call) or from the float64 polynomial
- * phase(i) = sum_k coef[k] ((i - i_ref)/rate)^k evaluated by Horner's rule
- * with individually rounded operations.  With power != 0 the input is
+ * phase(i) = sum_k coef[k] ((i - i_ref)/rate)^k (i_ref: sample index, possibly
+ * fractional, at which the polynomial's time argument is zero) evaluated in
+ * float64 by Horner's rule with individually rounded operations.  With power != 0 the input is
  * [n][inner/4][2] complex64 and the four polarization products are formed
  * on the fly.  sum[bin][n_phase][inner] float32 and count[bin][n_phase]
  * int64 are accumulated (+=). */
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
                   int64_t i_first, const int64_t* lo, const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,
-                  const double* coef, int ncoef, int64_t i_ref, double rate,
+                  const double* coef, int ncoef, double i_ref, double rate,
                   int n_phase, void* sum, void* count, void* stream);
+
+/* ---- Averaging: out[b][c] = sum[b][c] / count[b] (NaN for empty bins),
+ * the division Integrate._read_frame does (integration.py:268-269). */
+int bbt_average_exec(const void* sum, const void* count, void* out,
+                     int64_t n_bins, int64_t inner, void* stream);
+
+/* ---- Measurement helpers (not part of the reference surface).
+ * bbt_launch_count: kernels launched by this library so far.
+ * bbt_profile_enable(1): bracket every launch with CUDA events on its stream;
+ * bbt_profile_report: wait for them and write "kernel count total_ms" lines
+ * (NUL-terminated) into buf, clearing the records. */
+int64_t bbt_launch_count(void);
+int bbt_profile_enable(int on);
+int bbt_profile_report(char* buf, int64_t size);
 
 /* ---- Measurement helper (not part of the reference surface): copies
  * `rows` chunks of chunk_bytes, row_stride_bytes apart, for each of n_tiles

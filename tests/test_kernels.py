@@ -390,7 +390,7 @@ def test_integrate(backend, n, inner, ratio):
 
 def poly_phase(coef, i, i_ref, rate):
     """Oracle phase: Horner in float64, same operation order as the kernel."""
-    dt = (i - i_ref).astype(np.float64) / rate
+    dt = (i.astype(np.float64) - i_ref) / rate
     ph = np.full(dt.shape, coef[-1])
     for c in coef[-2::-1]:
         ph = ph * dt + c
@@ -412,7 +412,7 @@ def test_fold(backend, power, n_phase, n_tbin):
         xin = (rng.normal(size=(n, inner)) ** 2).astype('f4')
         x = xin
     offsets = np.linspace(7, n - 11, n_tbin + 1).round().astype(np.int64)
-    i_ref = -12345
+    i_ref = -12345.25
     want, wcount = orc.fold(
         xin, offsets, n_phase,
         lambda i: poly_phase(coef, i, i_ref, rate), 'left')

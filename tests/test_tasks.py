@@ -1,0 +1,528 @@
+"""The Task / FFTMaker API on top of the kernels, against the oracle.
+
+Runs on the host-thread emulation of the kernels (CPU tensors stand in for
+device buffers; test infrastructure only) and, marked ``gpu``, on the B200.
+The cases follow the reference's own tests where their inputs are synthetic
+(tests/test_dispersion.py, test_integration.py, fourier/tests/test_fourier.py).
+"""
+import numpy as np
+import pytest
+
+import bbt_oracle as orc
+
+from test_kernels import assert_voltage, assert_power, cnoise
+
+
+@pytest.fixture
+def bt(backend):
+    """The package, wired to the backend under test."""
+    import torch
+    import baseband_tasks_b200 as pkg
+    from baseband_tasks_b200 import _cabi
+    saved = (_cabi._LIB, _cabi._DEVICE)
+    if backend.name == 'emu':
+        _cabi._LIB = backend.lib
+        _cabi._DEVICE = torch.device('cpu')
+    else:
+        _cabi._LIB = backend.lib
+        _cabi._DEVICE = backend.device
+    yield pkg
+    _cabi._LIB, _cabi._DEVICE = saved
+
+
+START = None
+
+
+def start_time(bt):
+    return bt.Time(1289567655, 0.)   # 2010-11-12T13:14:15 in unix seconds
+
+
+# ------------------------------------------------------------------ fourier
+def test_fft_maker_registry(bt):
+    from baseband_tasks_b200.fourier import (FFT_MAKER_CLASSES, fft_maker,
+                                             CudaFFTMaker, FFTMakerBase)
+    assert FFT_MAKER_CLASSES['cuda'] is CudaFFTMaker
+    assert isinstance(fft_maker.get(), CudaFFTMaker)
+    default = fft_maker.system_default
+    other = CudaFFTMaker()
+    with fft_maker.set(other):
+        assert fft_maker.get() is other
+        with fft_maker.set('cuda'):
+            assert fft_maker.get() is not other
+        assert fft_maker.get() is other
+    assert fft_maker.get() is default
+    with pytest.raises(KeyError):
+        fft_maker.set('numpy')
+    with pytest.raises(TypeError):
+        fft_maker.set(other, threads=2)
+    with pytest.raises(ValueError):
+        class CudaFFTMaker(FFTMakerBase):  # noqa: F811  key already taken
+            pass
+    assert CudaFFTMaker.next_fast_len(130) == 256
+    assert CudaFFTMaker.next_fast_len(256) == 256
+    with pytest.raises(NotImplementedError):
+        fft_maker((7919,), 'c8')
+
+
+def test_fft_object(bt):
+    """After fourier/tests/test_fourier.py:89-166, in single precision."""
+    from baseband_tasks_b200.fourier import fft_maker
+    n = 4096
+    t = np.arange(n)
+    y = np.exp(2j * np.pi * 200. * t / n).astype('c8')
+    fft = fft_maker((n,), 'c8', sample_rate=1e3)
+    assert fft.direction == 'forward' and fft.axis == 0 and not fft.ortho
+    assert fft.time_shape == (n,) and fft.frequency_shape == (n,)
+    Y = fft(y)
+    assert isinstance(Y, np.ndarray) and Y.dtype == np.complex64
+    assert_voltage(Y, np.fft.fft(y))
+    assert np.argmax(np.abs(Y)) == 200
+    np.testing.assert_allclose(fft.frequency[200], 200. * 1e3 / n)
+    ifft = fft.inverse()
+    assert ifft.direction == 'backward' and ifft == fft.inverse()
+    assert ifft != fft
+    assert_voltage(ifft(Y), y)
+    # real, ortho, starting from the inverse
+    x = np.random.default_rng(1).normal(size=(8, n // 4, 3)).astype('f4')
+    irfft = fft_maker(x.shape, 'f4', direction='backward', axis=1, ortho=True)
+    rfft = irfft.inverse()
+    assert rfft.frequency_shape == (8, n // 8 + 1, 3)
+    assert rfft.frequency_dtype == np.dtype('c8')
+    X = rfft(x)
+    assert_voltage(X, np.fft.rfft(x, axis=1, norm='ortho').astype('c8'))
+    assert_voltage(irfft(X), x)
+    assert rfft.frequency.shape == (n // 8 + 1, 1)
+    # Parseval
+    np.testing.assert_allclose(np.sum(x.astype('f8') ** 2), (
+        np.sum(np.abs(X[:, 0]) ** 2) + 2 * np.sum(np.abs(X[:, 1:-1]) ** 2)
+        + np.sum(np.abs(X[:, -1]) ** 2)), rtol=1e-5)
+    with pytest.raises(ValueError):
+        fft(y[:10])
+    # device tensors stay on the device
+    d = __import__('baseband_tasks_b200')._buffers.as_device(y)
+    D = fft(d)
+    assert not isinstance(D, np.ndarray)
+    assert_voltage(D.cpu().numpy(), np.fft.fft(y))
+
+
+def test_fft_large_strided(bt):
+    from baseband_tasks_b200.fourier import fft_maker
+    x = cnoise(np.random.default_rng(3), (1 << 14, 2))
+    fft = fft_maker(x.shape, 'c8', axis=0)
+    assert_voltage(fft(x), np.fft.fft(x, axis=0))
+
+
+# --------------------------------------------------------------------- dm
+def test_dm(bt):
+    """tests/test_dm.py:33-73 of the reference."""
+    dm = bt.DispersionMeasure(29.1168)
+    assert abs(bt.DispersionMeasure(1.).time_delay(1e6) - 1. / 2.41e-4) < 1e-9
+    f, fref = np.array([320e6, 330e6]), 325e6
+    d = dm.dispersion_delay_constant * 29.1168
+    np.testing.assert_allclose(
+        dm.time_delay(f, fref), d * (1 / 320.**2 - 1 / 325.**2) *
+        np.array([1., 0]) + d * (1 / 330.**2 - 1 / 325.**2) *
+        np.array([0, 1.]), rtol=1e-13)
+    np.testing.assert_allclose(dm.phase_delay(f, fref),
+                               orc.dm_phase_delay(29.1168, f / 1e6, 325.),
+                               rtol=1e-13)
+    np.testing.assert_allclose(dm.phase_factor(f, fref),
+                               orc.dm_phase_factor(29.1168, f / 1e6, 325.),
+                               rtol=1e-6)
+    assert float(-dm) == -29.1168
+
+
+# ------------------------------------------------------------ dedispersion
+def noise_source(bt, n, sample_shape=(), rate=1e6, spf=1000, seed=1234,
+                 **kwargs):
+    return bt.NoiseGenerator((n,) + sample_shape, start_time(bt), rate,
+                             samples_per_frame=spf, dtype='c8', seed=seed,
+                             **kwargs)
+
+
+@pytest.mark.parametrize('shape,sideband,spf', [
+    ((), 1, 1024 - 28), ((2,), np.array([1, -1]), None)])
+def test_dedisperse_stream(bt, shape, sideband, spf):
+    n = 5000
+    dm = 3.
+    src = noise_source(bt, n, shape, frequency=300e6, sideband=sideband)
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    x = orc.noise_stream(1234, n, 1000, shape)
+    op = orc.DispersePlan(-dm, 300., sideband, 1., True, n, 1000, shape,
+                          samples_per_frame=spf, fast_len=orc.next_pow2)
+    assert dd.samples_per_frame == op.samples_per_frame
+    assert dd._ih_samples_per_frame == op.N
+    assert dd.shape == (op.n_out,) + shape
+    assert dd.dm == dm
+    assert abs((dd.start_time - src.start_time) - op.start_offset) < 1e-12
+    assert dd.sample_rate == src.sample_rate
+    want = orc.disperse(x, op)
+    got = dd.read()
+    assert got.dtype == np.complex64 and got.shape == want.shape
+    assert_voltage(got, want)
+    # Arbitrary reads: across frames, and the re-anchored last frame.
+    dd.seek(op.samples_per_frame - 10)
+    assert_voltage(dd.read(25), want[op.samples_per_frame - 10:
+                                     op.samples_per_frame + 15])
+    dd.seek(-7, 2)
+    assert dd.tell() == op.n_out - 7
+    assert_voltage(dd.read(7), want[-7:])
+    with pytest.raises(EOFError):
+        dd.read(1)
+    # phase factor as the reference defines it.
+    pf = dd.phase_factor
+    assert pf.shape == (op.N,) + shape
+    assert np.max(np.abs(pf - np.broadcast_to(op.phase_factor('c8'),
+                                              pf.shape))) < 2e-6
+    # task on one frame.
+    frame = dd.task(x[:op.N])
+    assert_voltage(frame, want[:op.samples_per_frame])
+    dd.close()
+    with pytest.raises(ValueError):
+        dd.read(1)
+
+
+def test_disperse_dedisperse_roundtrip(bt):
+    """tests/test_dispersion.py:103-124: giant pulse, disperse then
+    dedisperse gives it back."""
+    n = 40000
+    data = np.zeros((n, 2), 'c8')
+    data[16000] = 1.
+    src = bt.ArrayStream(data, start_time(bt), 128e3, samples_per_frame=1000,
+                         frequency=300e6, sideband=np.array([1, -1]))
+    dm = 1000. * 0.05 / 0.039342251 * (128e3 / 128e3) * 0.2
+    disp = bt.Disperse(src, dm, samples_per_frame=8192 - 4096)
+    dedisp = bt.Dedisperse(disp, dm, samples_per_frame=8192 - 4096)
+    assert dedisp.dm == dm and disp.dm == dm
+    out = dedisp.read()
+    off = round((dedisp.start_time - src.start_time) * 128e3)
+    want = data[off:off + out.shape[0]]
+    assert np.max(np.abs(out - want)) < 1e-2
+    # All the power of the dispersed pulse is spread out.
+    disp.seek(0)
+    d = disp.read()
+    assert np.max(np.abs(d)) < 0.2
+    np.testing.assert_allclose(np.sum(np.abs(d) ** 2, axis=0), 1., rtol=1e-3)
+
+
+def test_dedisperse_errors(bt):
+    src = noise_source(bt, 3000)
+    with pytest.raises(TypeError):
+        bt.Dedisperse(src, 1.)       # no frequency
+    with pytest.raises(ValueError):
+        noise_source(bt, 10, frequency=300e6)   # frequency without sideband
+
+
+# ------------------------------------------------------------------- chain
+def make_chain(bt, x, rate, freq, dm, n_chan, spf, device_input):
+    data = x
+    if device_input:
+        from baseband_tasks_b200 import _buffers
+        data = _buffers.as_device(x)
+    src = bt.ArrayStream(data, start_time(bt), rate, samples_per_frame=2048,
+                         frequency=freq, sideband=1,
+                         polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    ch = bt.Channelize(dd, n_chan)
+    pw = bt.Power(ch)
+    return src, dd, ch, pw
+
+
+@pytest.mark.parametrize('device_input', [False, True])
+def test_chain_dedisperse_channelize_power_integrate(bt, device_input):
+    rng = np.random.default_rng(11)
+    n, rate, dm, n_chan = 20000, 1e6, 3., 64
+    freq = np.array([[300e6], [301e6], [302e6]])
+    x = cnoise(rng, (n, 3, 2))
+    src, dd, ch, pw = make_chain(bt, x, rate, freq, dm, n_chan, 4096 - 600,
+                                 device_input)
+    op = orc.DispersePlan(-dm, freq / 1e6, 1, 1., True, n, 2048, (3, 2),
+                          samples_per_frame=4096 - 600,
+                          fast_len=orc.next_pow2)
+    y = orc.disperse(x, op)
+    spectra = orc.channelize(y, n_chan)
+    power = orc.power(spectra, axis=-1)
+    assert ch.shape == spectra.shape and pw.shape == power.shape
+    assert ch.sample_rate == rate / n_chan
+    np.testing.assert_array_equal(
+        ch.frequency, orc.channelize_frequency(freq, 1, n_chan, rate, False,
+                                               2))
+    assert list(pw.polarization) == ['XX', 'YY', 'XY', 'YX']
+    assert_voltage(ch.read(), spectra)
+    assert_power(pw.read(), power)
+    # Integrate over 2.26 spectra per bin: uneven bins, exact counts.
+    step = 2.26 * n_chan / rate
+    ip = orc.IntegratePlan(power.shape[0], rate / n_chan, step)
+    offsets = ip.offsets(np.arange(ip.n_out + 1))
+    want, wcount = orc.integrate(power, offsets)
+    it = bt.Integrate(pw, step, average=False)
+    assert it._fused == 'chanpow'
+    assert it.shape == (ip.n_out,) + power.shape[1:]
+    res = it.read()
+    np.testing.assert_array_equal(res['count'][:, 0, 0, 0], wcount.ravel())
+    assert_power(res['data'], want)
+    avg = bt.Integrate(pw, step).read()
+    assert_power(avg, want / wcount)
+    # Unfused path gives the same.
+    it2 = bt.Integrate(pw, step, average=False)
+    it2._fused, it2._src, it2._src_ratio = None, pw, 1
+    res2 = it2.read()
+    np.testing.assert_array_equal(res2['count'], res['count'])
+    assert_power(res2['data'], want)
+    # Reading in pieces and from an offset.
+    it.seek(3)
+    part = it.read(4)
+    np.testing.assert_array_equal(part['count'], res['count'][3:7])
+    assert_power(part['data'], want[3:7])
+
+
+def test_square_and_power_axes(bt):
+    rng = np.random.default_rng(12)
+    x = cnoise(rng, (1000, 2, 3))
+    src = bt.ArrayStream(x, start_time(bt), 1e3, samples_per_frame=100,
+                         polarization=np.array([['L'], ['R']]))
+    sq = bt.Square(src)
+    assert sq.polarization.tolist() == [['LL'], ['RR']]
+    assert sq.dtype == np.float32
+    assert_power(sq.read(), orc.square(x))
+    pw = bt.Power(src)
+    assert pw.shape == (1000, 4, 3)
+    assert pw.polarization.tolist() == [['LL'], ['RR'], ['LR'], ['RL']]
+    pw.seek(95)
+    assert_power(pw.read(10), orc.power(x, axis=1)[95:105])
+    with pytest.raises(ValueError):
+        bt.Power(src, polarization=['LL', 'RR', 'LR'])
+    real = bt.ArrayStream(x.real.copy(), start_time(bt), 1e3,
+                          polarization=np.array([['L'], ['R']]))
+    with pytest.raises(ValueError):
+        bt.Power(real)
+    assert_power(bt.Square(real).read(), x.real ** 2)
+
+
+def test_dechannelize_roundtrip(bt):
+    rng = np.random.default_rng(13)
+    x = cnoise(rng, (64 * 33, 2))
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=64,
+                         frequency=300e6, sideband=np.array([1, -1]))
+    ch = bt.Channelize(src, 64, samples_per_frame=16)
+    assert ch.shape == (33 // 16 * 16, 64, 2)
+    dc = ch.inverse(ch)
+    assert dc.shape == (32 * 64, 2)
+    assert dc.sample_rate == src.sample_rate
+    assert_voltage(dc.read(), x[:32 * 64])
+    np.testing.assert_array_equal(dc.frequency, src.frequency)
+
+
+# ---------------------------------------------------------------- integrate
+def fake_pulsar(bt, dtype='f4'):
+    """tests/test_integration.py:17-43: 16000x2 @10 kHz, a pulse every 125."""
+    data = np.full((16000, 2), 0.125, dtype)
+    data[::125] = 10.
+    return data, bt.ArrayStream(data, start_time(bt), 1e4,
+                                samples_per_frame=200)
+
+
+@pytest.mark.parametrize('spf', [1, 4, 10])
+def test_integrate_integer_step(bt, spf):
+    data, src = fake_pulsar(bt)
+    it = bt.Integrate(src, 125, samples_per_frame=spf)
+    assert it.shape == (128, 2) and it.sample_rate == 1e4 / 125
+    assert it.start_time == src.start_time
+    out = it.read()
+    want = data.reshape(-1, 125, 2).mean(1)
+    np.testing.assert_allclose(out, want, rtol=1e-6)
+    it.seek(100)
+    assert abs((it.time - src.start_time) - 100 * 125 / 1e4) < 1e-12
+    np.testing.assert_allclose(it.read(3), want[100:103], rtol=1e-6)
+
+
+def test_integrate_time_step_counts(bt):
+    """tests/test_integration.py:212-254: 2.26-sample bins."""
+    data, src = fake_pulsar(bt)
+    step = 2.26 / 1e4
+    it = bt.Integrate(src, step, average=False)
+    assert it.dtype.names == ('data', 'count')
+    out = it.read(8)
+    np.testing.assert_array_equal(out['count'][:, 0],
+                                  [2, 3, 2, 2, 2, 3, 2, 2])
+    ip = orc.IntegratePlan(16000, 1e4, step)
+    assert it.shape[0] == ip.n_out
+    offsets = ip.offsets(np.arange(ip.n_out + 1))
+    want, wcount = orc.integrate(data, offsets)
+    it.seek(0)
+    full = it.read()
+    np.testing.assert_array_equal(full['count'],
+                                  np.broadcast_to(wcount, full.shape))
+    np.testing.assert_allclose(full['data'], want, rtol=1e-6)
+    # start at an offset and at a time
+    it2 = bt.Integrate(src, 10, start=25)
+    assert it2.shape[0] == int((16000 - 25) / 10 + 0.5 / 10)
+    np.testing.assert_allclose(it2.read(2),
+                               data[25:45].reshape(2, 10, 2).mean(1),
+                               rtol=1e-6)
+    with pytest.raises(ValueError):
+        bt.Integrate(src, 10, start=-1)
+
+
+def test_integrate_whole_stream_complex(bt):
+    rng = np.random.default_rng(5)
+    x = cnoise(rng, (3000, 3))
+    src = bt.ArrayStream(x, start_time(bt), 1e3, samples_per_frame=100)
+    it = bt.Integrate(src)
+    assert it.shape == (1, 3) and it.dtype == np.complex64
+    assert_voltage(it.read(), x.mean(0, keepdims=True), tol=1e-4)
+
+
+# --------------------------------------------------------------------- fold
+@pytest.mark.parametrize('use_poly', [True, False])
+@pytest.mark.parametrize('step,spf', [(None, 1), (0.2, 1), (0.2, 3)])
+def test_fold(bt, use_poly, step, spf):
+    data, src = fake_pulsar(bt)
+    n_phase = 50
+    f0 = 1e4 / 125 * 1.0000123
+    t0 = src.start_time + 0.0123
+    poly = bt.PolynomialPhase([0.1, f0, -1e-3], t0)
+    rate = 1e4
+    i_ref = poly.i_ref(src.start_time, rate)
+    if use_poly:
+        phase = poly
+    else:
+        # Any callable; evaluate with the same index-based convention so
+        # the oracle below applies to both.
+        def phase(t):
+            idx = np.round((t - src.start_time) * rate)
+            return poly.of_index(idx, i_ref, rate)
+    fold = bt.Fold(src, n_phase, phase, step, samples_per_frame=spf,
+                   average=False)
+    if step is None:
+        assert fold.shape == (1, n_phase, 2)
+        offsets = np.array([0, 16000])
+        frames = [offsets]
+    else:
+        ip = orc.IntegratePlan(16000, rate, step)
+        assert fold.shape == (ip.n_out, n_phase, 2)
+        offsets = ip.offsets(np.arange(ip.n_out + 1))
+        frames = [offsets[i:i + spf + 1]
+                  for i in range(0, ip.n_out, spf)]
+    want = []
+    wcount = []
+    for fo in frames:
+        d, c = orc.fold(data, fo, n_phase,
+                        lambda i: poly.of_index(i, i_ref, rate), 'left')
+        want.append(d)
+        wcount.append(c)
+    want = np.concatenate(want)
+    wcount = np.concatenate(wcount)
+    out = fold.read()
+    np.testing.assert_array_equal(out['count'],
+                                  np.broadcast_to(wcount, out.shape))
+    np.testing.assert_allclose(out['data'], want, rtol=1e-5)
+    assert out['count'].sum() == (offsets[-1] - offsets[0]) * 2
+    avg = bt.Fold(src, n_phase, phase, step, samples_per_frame=spf).read()
+    with np.errstate(invalid='ignore', divide='ignore'):
+        np.testing.assert_allclose(avg, want / wcount, rtol=1e-5)
+
+
+def test_fold_power_fused(bt):
+    rng = np.random.default_rng(21)
+    x = cnoise(rng, (6000, 3, 2))
+    src = bt.ArrayStream(x, start_time(bt), 1e4, samples_per_frame=500,
+                         polarization=np.array(['X', 'Y']))
+    pw = bt.Power(src)
+    poly = bt.PolynomialPhase([0., 29.946923, -3.77535e-10 / 2],
+                              src.start_time)
+    fold = bt.Fold(pw, 32, poly, average=False)
+    assert fold._fused == 'power'
+    out = fold.read()
+    power = orc.power(x, axis=-1)
+    want, wcount = orc.fold(power, np.array([0, 6000]), 32,
+                            lambda i: poly.of_index(i, 0., 1e4))
+    np.testing.assert_array_equal(out['count'],
+                                  np.broadcast_to(wcount, out.shape))
+    assert_power(out['data'], want)
+
+
+# --------------------------------------------------------------- framework
+def test_base_stream_semantics(bt):
+    """read/seek/tell/time, slicing and errors (tests/test_base.py)."""
+    x = cnoise(np.random.default_rng(2), (1000, 4))
+    src = bt.ArrayStream(x, start_time(bt), 1e3, samples_per_frame=100,
+                         frequency=np.array([300e6, 300e6, 316e6, 316e6]),
+                         sideband=np.array([-1, 1, -1, 1]))
+    assert src.sample_shape == (4,) and src.size == 4000 and src.ndim == 2
+    assert src.complex_data and src.dtype == np.complex64
+    assert src.sideband.dtype == np.int8
+    assert src.stop_time - src.start_time == 1.
+    assert src.seek(10) == 10 and src.seek(5, 1) == 15
+    assert src.seek(-5, 'end') == 995
+    assert src.seek(src.start_time + 0.5) == 500
+    assert src.seek(0.25) == 250      # time offset in seconds
+    assert src.tell(unit='time') - src.start_time == 0.25
+    with pytest.raises(ValueError):
+        src.seek(0, 3)
+    sa = bt.SetAttribute(src, frequency=np.array([1e6, 2e6, 3e6, 4e6]),
+                         sideband=1)
+    assert sa.frequency.tolist() == [1e6, 2e6, 3e6, 4e6]
+    assert np.all(sa.sideband == 1)
+    sa.seek(20)
+    np.testing.assert_array_equal(sa.read(5), x[20:25])
+    task = bt.Task(src, lambda data: data * 2, samples_per_frame=50)
+    task.seek(120)
+    np.testing.assert_array_equal(task.read(100), x[120:220] * 2)
+    sl = src[100:200, 1]
+    assert sl.shape == (100,) and sl.frequency == 300e6
+    np.testing.assert_array_equal(sl.read(), x[100:200, 1])
+    np.testing.assert_array_equal(np.array(src[10:12]), x[10:12])
+    with pytest.raises(AssertionError):
+        src.read(out=np.empty((3, 5), 'c8'))
+    with pytest.raises(TypeError):
+        bt.ArrayStream(x, start_time(bt), 1e3, bla=1)
+    assert 'ArrayStream' in repr(src) and 'ih' in repr(sa)
+
+
+def test_padded_task_base_framing(bt):
+    """tests/test_base.py:491-546: PaddedTaskBase sizes."""
+    from baseband_tasks_b200.base import PaddedTaskBase
+    x = np.arange(40000.).astype('f4')
+    src = bt.ArrayStream(x, start_time(bt), 1e3, samples_per_frame=20000)
+
+    class SquareHat(PaddedTaskBase):
+        def __init__(self, ih, n, **kwargs):
+            self._n = n
+            super().__init__(ih, pad_start=n - 1, **kwargs)
+
+        def task(self, data):
+            size = data.shape[0] - self._n + 1
+            return sum(data[i:i + size] for i in range(self._n))
+
+    sh = SquareHat(src, 3)
+    assert sh._ih_samples_per_frame == 20000 and sh.samples_per_frame == 19998
+    assert sh.shape == (39998,)
+    assert abs((sh.start_time - src.start_time) - 2 / 1e3) < 1e-12
+    want = x[:-2] + x[1:-1] + x[2:]
+    np.testing.assert_array_equal(sh.read(10), want[:10])
+    sh.seek(-10, 2)
+    np.testing.assert_array_equal(sh.read(10), want[-10:])
+    nfl = orc.next_fast_len
+    assert SquareHat(src, 3, samples_per_frame=128,
+                     next_fast_len=nfl).samples_per_frame == 133
+    assert SquareHat(src, 5, samples_per_frame=128,
+                     next_fast_len=nfl)._ih_samples_per_frame == 135
+    with pytest.raises(ValueError):
+        SquareHat(src, 0)
+    with pytest.warns(UserWarning, match='inefficient'):
+        SquareHat(src, 10, samples_per_frame=8)
+
+
+def test_noise_generator_reproducible(bt):
+    """tests/test_generators.py:253-316."""
+    nh = noise_source(bt, 10000, (2,), spf=1000, seed=12345)
+    a = nh.read(2500)
+    nh.seek(1500)
+    b = nh.read(1000)
+    np.testing.assert_array_equal(a[1500:], b)
+    np.testing.assert_array_equal(
+        a, orc.noise_stream(12345, 2500, 1000, (2,)))
+    nh.seek(0)
+    full = nh.read()
+    assert abs(full.real.std() - 1.) < 0.02 and abs(full.mean()) < 0.02
