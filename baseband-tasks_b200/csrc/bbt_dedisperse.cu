@@ -1,0 +1,364 @@
+// C-ABI implementation (see include/bbt_b200.h): coherent (de)dispersion.
+#include "common.cuh"
+#include "kernels_dedisperse.cuh"
+
+using namespace bbt;
+
+struct bbt_dedisperse_plan {
+  int64_t n, n_series, pad_start, n_valid, n_chirp;
+  int log2n, log2n1, log2n2;
+  int planar;      // work-buffer layout of the three-pass split
+  int col_e32;     // 32 elements per thread in short column FFTs
+  int row16;       // 16 elements per thread in the row FFTs
+  const cf* tw;
+  cf* big_lo;
+  cf* big_hi;
+  cf* chirp;        // [n_chirp][n1][n2]
+  int* series_map;  // device
+};
+
+namespace {
+
+constexpr int kColThreads = 512;
+
+// Elements per thread of the column FFTs.
+template <int L1, bool E32>
+struct ColCfg {
+  static constexpr int LOG2E = L1 <= 4 ? L1 : ((L1 <= 8 && !E32) ? 4 : 5);
+  using type = FftCfg<L1, LOG2E, kColThreads>;
+};
+
+int col_lanes(int l1, bool e32) {
+  const int log2e = l1 <= 4 ? l1 : ((l1 <= 8 && !e32) ? 4 : 5);
+  return kColThreads >> (l1 - log2e);
+}
+
+template <int L1, bool E32>
+int launch_dd_col(bool inverse, const DdArgs& a, int64_t n_frames,
+                  bbt_stream_t st) {
+  using C = typename ColCfg<L1, E32>::type;
+  const int64_t cols = (a.N >> L1) * a.S;
+  dim3 grid((unsigned)ceil_div(cols, C::G), (unsigned)n_frames);
+  const size_t smem = C::SMEM_BYTES;
+  auto kern = inverse ? dd_col_inv_kernel<C> : dd_col_fwd_kernel<C>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = inverse ? "dd_col_inv" : "dd_col_fwd";
+  BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
+  return check_launch("dedispersion column kernel");
+}
+
+// ROW16: 16 elements per thread in 1024-thread CTAs instead of 32 in 512 (or
+// 256 for planar rows below 2^14 points, two CTAs per SM).
+template <int L2, bool PLANAR, bool ROW16>
+int launch_dd_row(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
+  using C = FftCfg<L2, ROW16 ? 4 : 5,
+                   ROW16 ? 1024 : ((PLANAR && L2 < 14) ? 256 : 512)>;
+  const int64_t n1 = a.N >> L2;
+  int64_t blocks;
+  if (PLANAR) {
+    blocks = ceil_div(n1 * a.S, C::G);
+  } else {
+    const int sc = a.S < C::G ? (int)a.S : C::G;
+    const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
+    blocks = ceil_div(n1, rpc) * ceil_div(a.S, sc);
+  }
+  dim3 grid((unsigned)blocks, (unsigned)n_frames);
+  const size_t smem = C::SMEM_BYTES;
+  auto kern = dd_row_kernel<C, PLANAR>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "dd_row";
+  BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
+  return check_launch("dedispersion row kernel");
+}
+
+template <int L, bool LANEFAST>
+int launch_dd_small(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
+  using D = DefaultCfg<L>;
+  using C = FftCfg<L, D::LOG2E, LANEFAST ? 512 : D::THREADS>;
+  const int64_t blocks = ceil_div(n_frames * a.S, C::G);
+  const size_t smem = C::SMEM_BYTES;
+  auto kern = dd_small_kernel<C, LANEFAST>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "dd_small";
+  BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a,
+             (long long)n_frames);
+  return check_launch("dedispersion kernel");
+}
+
+#define BBT_FOR_ROW(L, F)   \
+  switch (L) {              \
+    case 10: F(10); break;  \
+    case 11: F(11); break;  \
+    case 12: F(12); break;  \
+    case 13: F(13); break;  \
+    case 14: F(14); break;  \
+    default: break;         \
+  }
+
+}  // namespace
+
+extern "C" {
+
+int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
+                               int64_t n_series, int64_t pad_start,
+                               int64_t n_valid, int64_t n_chirp,
+                               const int32_t* series_map,
+                               const double* freq_mhz, const double* fref_mhz,
+                               const int8_t* sideband, double dm,
+                               double rate_mhz, double sample_offset,
+                               int hint) {
+  if (!plan) return fail(BBT_EINVAL, "null plan pointer");
+  *plan = nullptr;
+  if (n < 2 || !is_pow2(n))
+    return fail(BBT_EUNSUPPORTED, "frame length must be a power of two >= 2");
+  const int l = ilog2(n);
+  if (l > 26) return fail(BBT_EUNSUPPORTED, "frame length above 2^26");
+  if (n_series < 1 || n_chirp < 1 || pad_start < 0 || n_valid < 1 ||
+      pad_start + n_valid > n)
+    return fail(BBT_EINVAL, "bad dedispersion geometry");
+  if (!series_map) return fail(BBT_EINVAL, "null series_map");
+  for (int64_t s = 0; s < n_series; ++s)
+    if (series_map[s] < 0 || series_map[s] >= n_chirp)
+      return fail(BBT_EINVAL, "series_map entry out of range");
+  bbt_dedisperse_plan* p = new bbt_dedisperse_plan();
+  p->n = n;
+  p->n_series = n_series;
+  p->pad_start = pad_start;
+  p->n_valid = n_valid;
+  p->n_chirp = n_chirp;
+  p->log2n = l;
+  p->big_lo = p->big_hi = p->chirp = nullptr;
+  p->series_map = nullptr;
+  p->planar = 1;
+  p->col_e32 = (hint >> 10) & 1;
+  p->row16 = (hint >> 11) & 1;
+  const int hint_l1 = hint & 0xff;
+  const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;
+  if (l <= kLog2TwiddleTable && (n_series == 1 || l <= 10) && !hint_l1) {
+    p->log2n1 = 0;  // single pass
+    p->log2n2 = l;
+  } else {
+    // Planar candidate: longest row the row kernel takes.
+    int l2 = l - 1 < 14 ? l - 1 : 14;
+    if (l2 < 10) l2 = 10;
+    int l1 = l - l2;
+    bool planar = true;
+    if (n_series > 1 && !force_planar) {
+      const int tn = col_lanes(l1, p->col_e32) / (int)std::min<int64_t>(
+                                                     n_series, 1 << 20);
+      // Rows of >= 8 interleaved series move in 64-byte runs as they are.
+      if (((tn < 8 || n_series >= 8) && l - 10 <= 12) || force_inter) {
+        planar = false;
+        l2 = 10;
+        l1 = l - 10;
+      }
+    }
+    if (hint_l1) {
+      l1 = hint_l1;
+      l2 = l - l1;
+    }
+    if (l1 < 1 || l1 > 14 || l2 < 10 || l2 > 14) {
+      delete p;
+      return fail(BBT_EUNSUPPORTED, "unsupported split of the frame length");
+    }
+    p->log2n1 = l1;
+    p->log2n2 = l2;
+    p->planar = planar ? 1 : 0;
+  }
+  p->tw = twiddle_table();
+  void* d = nullptr;
+  int rc = BBT_OK;
+  if (!p->tw) rc = BBT_ENOMEM;
+  if (!rc && dev_alloc(&d, n_chirp * n * sizeof(cf))) rc = BBT_ENOMEM;
+  p->chirp = static_cast<cf*>(d);
+  d = nullptr;
+  if (!rc && dev_alloc(&d, n_series * sizeof(int))) rc = BBT_ENOMEM;
+  p->series_map = static_cast<int*>(d);
+  if (!rc && h2d(p->series_map, series_map, n_series * sizeof(int), 0))
+    rc = BBT_ECUDA;
+  if (!rc && p->log2n1 > 0) {
+    p->big_lo = make_roots(kTwiddleTable, (double)n);
+    const int64_t nhi = std::max<int64_t>(1, n >> kLog2TwiddleTable);
+    p->big_hi = make_roots(nhi, (double)n / (double)kTwiddleTable);
+    if (!p->big_lo || !p->big_hi) rc = BBT_ENOMEM;
+  }
+  if (rc) {
+    bbt_dedisperse_plan_destroy(p);
+    return fail(rc, "cannot allocate dedispersion plan tables");
+  }
+  if (freq_mhz && fref_mhz && sideband) {
+    // Chirp parameters to the device, then one float64 kernel.
+    void *dfreq = nullptr, *dref = nullptr, *dsb = nullptr;
+    if (dev_alloc(&dfreq, n_chirp * sizeof(double)) ||
+        dev_alloc(&dref, n_chirp * sizeof(double)) ||
+        dev_alloc(&dsb, n_chirp) ||
+        h2d(dfreq, freq_mhz, n_chirp * sizeof(double), 0) ||
+        h2d(dref, fref_mhz, n_chirp * sizeof(double), 0) ||
+        h2d(dsb, sideband, n_chirp, 0)) {
+      bbt_dedisperse_plan_destroy(p);
+      return fail(BBT_ENOMEM, "cannot stage chirp parameters");
+    }
+    ChirpArgs ca;
+    ca.chirp = p->chirp;
+    ca.freq_mhz = static_cast<const double*>(dfreq);
+    ca.fref_mhz = static_cast<const double*>(dref);
+    ca.sideband = static_cast<const signed char*>(dsb);
+    ca.N = n;
+    ca.n1 = int64_t(1) << p->log2n1;
+    ca.n_chirp = n_chirp;
+    ca.d = dm / 2.41e-4;  // dm.py:37
+    ca.rate_mhz = rate_mhz;
+    ca.sample_offset = sample_offset;
+    const unsigned blocks =
+        (unsigned)std::min<int64_t>(ceil_div(n_chirp * n, 256), 148 * 32);
+    BBT_LAUNCH(chirp_kernel, dim3(blocks), dim3(256), 0, (bbt_stream_t)0, ca);
+    rc = check_launch("chirp kernel");
+#if !defined(BBT_EMULATE)
+    if (!rc && cudaStreamSynchronize(0) != cudaSuccess)
+      rc = fail(BBT_ECUDA, "chirp kernel failed");
+#endif
+    dev_free(dfreq);
+    dev_free(dref);
+    dev_free(dsb);
+    if (rc) {
+      bbt_dedisperse_plan_destroy(p);
+      return rc;
+    }
+  }
+  *plan = p;
+  return BBT_OK;
+}
+
+int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* p,
+                                     const void* host_response) {
+  if (!p || !host_response) return fail(BBT_EINVAL, "null argument");
+  const int64_t total = p->n_chirp * p->n;
+  void* tmp = nullptr;
+  if (dev_alloc(&tmp, total * sizeof(cf)))
+    return fail(BBT_ENOMEM, "cannot stage response");
+  int rc = BBT_OK;
+  if (h2d(tmp, host_response, total * sizeof(cf), 0)) rc = BBT_ECUDA;
+  if (!rc) {
+    const unsigned blocks =
+        (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+    BBT_LAUNCH(chirp_scatter_kernel, dim3(blocks), dim3(256), 0,
+               (bbt_stream_t)0, p->chirp, static_cast<const cf*>(tmp), p->n,
+               int64_t(1) << p->log2n1, p->n_chirp);
+    rc = check_launch("response scatter kernel");
+#if !defined(BBT_EMULATE)
+    if (!rc && cudaStreamSynchronize(0) != cudaSuccess)
+      rc = fail(BBT_ECUDA, "response scatter failed");
+#endif
+  }
+  dev_free(tmp);
+  return rc;
+}
+
+int bbt_dedisperse_plan_get_response(const bbt_dedisperse_plan* p,
+                                     void* host_response) {
+  if (!p || !host_response) return fail(BBT_EINVAL, "null argument");
+  const int64_t n1 = int64_t(1) << p->log2n1, n2 = p->n / n1;
+  std::vector<cf> tmp(p->n_chirp * p->n);
+#if defined(BBT_EMULATE)
+  memcpy(tmp.data(), p->chirp, tmp.size() * sizeof(cf));
+#else
+  if (cudaMemcpy(tmp.data(), p->chirp, tmp.size() * sizeof(cf),
+                 cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(BBT_ECUDA, "cannot copy chirp to host");
+#endif
+  cf* out = static_cast<cf*>(host_response);
+  for (int64_t c = 0; c < p->n_chirp; ++c)
+    for (int64_t k1 = 0; k1 < n1; ++k1)
+      for (int64_t k2 = 0; k2 < n2; ++k2)
+        out[c * p->n + k1 + n1 * k2] = tmp[c * p->n + k1 * n2 + k2];
+  return BBT_OK;
+}
+
+int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* p,
+                                  int64_t n_frames) {
+  if (!p || p->log2n1 == 0) return 0;
+  return n_frames * p->n * p->n_series * (int64_t)sizeof(cf);
+}
+
+int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
+                        int64_t in_frame_stride, int64_t n_frames,
+                        int64_t skip, void* out, int64_t out_frame_stride,
+                        void* work, void* stream) {
+  if (!p || !in || !out) return fail(BBT_EINVAL, "null argument");
+  if (n_frames <= 0) return BBT_OK;
+  if (n_frames > 65535) return fail(BBT_EUNSUPPORTED, "too many frames per call");
+  if (skip < 0 || skip >= p->n_valid) return fail(BBT_EINVAL, "bad skip");
+  bbt_stream_t st = as_stream(stream);
+  DdArgs a;
+  a.in = static_cast<const cf*>(in);
+  a.out = static_cast<cf*>(out);
+  a.work = static_cast<cf*>(work);
+  a.tw = p->tw;
+  a.big = BigTwiddle{p->big_lo, p->big_hi};
+  a.chirp = p->chirp;
+  a.series_map = p->series_map;
+  a.in_frame_stride = in_frame_stride;
+  a.out_frame_stride = out_frame_stride;
+  a.N = p->n;
+  a.S = p->n_series;
+  a.log2n1 = p->log2n1;
+  a.log2n2 = p->log2n2;
+  a.planar = p->planar;
+  a.lo = (p->pad_start + skip) * p->n_series;
+  a.hi = (p->pad_start + p->n_valid) * p->n_series;
+  // Valid samples are stored from out + f*stride on, i.e. sample
+  // pad_start + skip lands at offset 0.
+  a.out_shift = (p->pad_start + skip) * p->n_series;
+  a.scale = (float)(1.0 / (double)p->n);
+  a.ahead = sm_count();
+  int rc = BBT_EUNSUPPORTED;
+  if (p->log2n1 == 0) {
+    const bool lanefast = p->n_series > 1;
+#define F(L)                                                        \
+  rc = lanefast ? launch_dd_small<L, true>(a, n_frames, st)         \
+                : launch_dd_small<L, false>(a, n_frames, st)
+    BBT_FOR_LOG2(p->log2n2, F)
+#undef F
+    return rc;
+  }
+  if (!work) return fail(BBT_EINVAL, "dedispersion needs a work buffer");
+  const bool e32 = p->col_e32;
+#define F(L)                                                         \
+  rc = e32 ? launch_dd_col<L, true>(false, a, n_frames, st)          \
+           : launch_dd_col<L, false>(false, a, n_frames, st)
+  BBT_FOR_LOG2(p->log2n1, F)
+#undef F
+  if (rc) return rc;
+  rc = BBT_EUNSUPPORTED;
+#define F(L)                                                           \
+  rc = p->planar ? (p->row16 ? launch_dd_row<L, true, true>(a, n_frames, st)   \
+                             : launch_dd_row<L, true, false>(a, n_frames, st)) \
+                 : (p->row16                                                   \
+                        ? launch_dd_row<L, false, true>(a, n_frames, st)       \
+                        : launch_dd_row<L, false, false>(a, n_frames, st))
+  BBT_FOR_ROW(p->log2n2, F)
+#undef F
+  if (rc) return rc;
+  rc = BBT_EUNSUPPORTED;
+#define F(L)                                                         \
+  rc = e32 ? launch_dd_col<L, true>(true, a, n_frames, st)           \
+           : launch_dd_col<L, false>(true, a, n_frames, st)
+  BBT_FOR_LOG2(p->log2n1, F)
+#undef F
+  return rc;
+}
+
+int bbt_dedisperse_plan_destroy(bbt_dedisperse_plan* p) {
+  if (!p) return BBT_OK;
+  if (p->big_lo) dev_free(p->big_lo);
+  if (p->big_hi) dev_free(p->big_hi);
+  if (p->chirp) dev_free(p->chirp);
+  if (p->series_map) dev_free(p->series_map);
+  delete p;
+  return BBT_OK;
+}
+
+}  // extern "C"

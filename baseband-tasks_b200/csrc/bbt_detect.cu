@@ -1,0 +1,193 @@
+// C-ABI implementation (see include/bbt_b200.h): detection, integration, fold.
+#include "common.cuh"
+#include "kernels_detect.cuh"
+
+using namespace bbt;
+
+extern "C" {
+
+// ----------------------------------------------------------------- detection
+int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
+                   void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (a <= 0 || b <= 0) return BBT_OK;
+  BBT_LAUNCH(power_kernel, dim3(grid_for(a * b, 256)), dim3(256), 0,
+             as_stream(stream), static_cast<const cf*>(in),
+             static_cast<float*>(out), (long long)a, (long long)b);
+  return check_launch("power kernel");
+}
+
+int bbt_square_exec(const void* in, void* out, int64_t n, int is_complex,
+                    void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (n <= 0) return BBT_OK;
+  BBT_LAUNCH(square_kernel, dim3(grid_for(n, 256)), dim3(256), 0,
+             as_stream(stream), static_cast<const float*>(in),
+             static_cast<float*>(out), (long long)n, is_complex);
+  return check_launch("square kernel");
+}
+
+}  // extern "C"
+namespace {
+// Two transforms (both polarizations) live in each thread: 16 elements each.
+template <int L>
+using ChanCfg = FftCfg<L, (L < 4 ? L : 4), 256>;
+
+template <int L, bool LANEFAST, bool INTEGRATE>
+int launch_chanpow(const ChanPowArgs& a, int64_t n_bins, bbt_stream_t st) {
+  using C = ChanCfg<L>;
+  const int64_t blocks = ceil_div(a.msub * a.M, C::G);
+  dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
+  const size_t smem = 2 * C::SMEM_BYTES;
+  auto kern = chanpow_kernel<C, LANEFAST, INTEGRATE>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = INTEGRATE ? "chanpow_integrate" : "chanpow";
+  BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
+  return check_launch("channelize-power kernel");
+}
+
+template <bool INTEGRATE>
+int run_chanpow(int log2n, ChanPowArgs& a, int64_t n_bins, int64_t max_width,
+                bbt_stream_t st) {
+  int rc = BBT_EUNSUPPORTED;
+  const bool lanefast = a.M > 1;
+#define F(L)                                                                 \
+  {                                                                          \
+    const int64_t g = ChanCfg<L>::G;                                          \
+    const int64_t want = (int64_t)sm_count() * 8 * g;                        \
+    int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));           \
+    if (msub > max_width) msub = max_width;                                  \
+    if (msub < 1) msub = 1;                                                  \
+    a.msub = msub;                                                           \
+    rc = lanefast ? launch_chanpow<L, true, INTEGRATE>(a, n_bins, st)        \
+                  : launch_chanpow<L, false, INTEGRATE>(a, n_bins, st);      \
+  }
+  BBT_FOR_LOG2(log2n, F)
+#undef F
+  if (rc == BBT_EUNSUPPORTED)
+    fail(rc, "channelizer length must be a power of two in [2, 16384]");
+  return rc;
+}
+}  // namespace
+extern "C" {
+
+int bbt_channelize_power_exec(const void* in, void* out, int64_t n, int64_t m,
+                              int64_t n_spec, void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (!is_pow2(n) || n < 2 || m < 1) return fail(BBT_EUNSUPPORTED, "bad channelizer shape");
+  if (n_spec <= 0) return BBT_OK;
+  ChanPowArgs a{};
+  a.in = static_cast<const cf2*>(in);
+  a.out = static_cast<float*>(out);
+  a.tw = twiddle_table();
+  a.M = m;
+  a.n_spec = n_spec;
+  return run_chanpow<false>(ilog2(n), a, 1, n_spec, as_stream(stream));
+}
+
+int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
+                                        int64_t n_spec, int64_t j_first,
+                                        const int64_t* offsets,
+                                        int64_t b_first, int64_t n_bins,
+                                        void* sum, void* count, void* stream) {
+  if (!in || !sum || !count || !offsets) return fail(BBT_EINVAL, "null argument");
+  if (!is_pow2(n) || n < 2 || m < 1) return fail(BBT_EUNSUPPORTED, "bad channelizer shape");
+  if (n_spec <= 0 || n_bins <= 0) return BBT_OK;
+  if (n_bins > 65535) return fail(BBT_EUNSUPPORTED, "too many bins per call");
+  ChanPowArgs a{};
+  a.in = static_cast<const cf2*>(in);
+  a.out = static_cast<float*>(sum);
+  a.count = static_cast<unsigned long long*>(count);
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.tw = twiddle_table();
+  a.M = m;
+  a.n_spec = n_spec;
+  a.j_first = j_first;
+  a.b_first = b_first;
+  return run_chanpow<true>(ilog2(n), a, n_bins,
+                           std::max<int64_t>(1, ceil_div(n_spec, n_bins)),
+                           as_stream(stream));
+}
+
+int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
+                       int64_t i_first, const int64_t* offsets,
+                       int64_t b_first, int64_t n_bins, void* sum, void* count,
+                       void* stream) {
+  if (!in || !sum || !count || !offsets) return fail(BBT_EINVAL, "null argument");
+  if (n <= 0 || n_bins <= 0 || inner <= 0) return BBT_OK;
+  if (n_bins > 65535) return fail(BBT_EUNSUPPORTED, "too many bins per call");
+  IntegrateArgs a;
+  a.in = static_cast<const float*>(in);
+  a.sum = static_cast<float*>(sum);
+  a.count = static_cast<unsigned long long*>(count);
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.inner = inner;
+  a.n = n;
+  a.i_first = i_first;
+  a.b_first = b_first;
+  const int64_t want = (int64_t)sm_count() * 2048;
+  int64_t msub = ceil_div(want, inner * n_bins);
+  msub = std::max<int64_t>(1, std::min<int64_t>(msub, ceil_div(n, n_bins)));
+  a.msub = msub;
+  dim3 grid((unsigned)ceil_div(msub * inner, 256), (unsigned)n_bins);
+  BBT_LAUNCH(integrate_kernel, grid, dim3(256), 0, as_stream(stream), a);
+  return check_launch("integrate kernel");
+}
+
+int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
+                  int64_t i_first, const int64_t* lo, const int64_t* hi,
+                  int64_t b_first, int64_t n_bins, const int32_t* pbin,
+                  const double* coef, int ncoef, double i_ref, double rate,
+                  int n_phase, void* sum, void* count, void* stream) {
+  if (!in || !sum || !count || !lo || !hi) return fail(BBT_EINVAL, "null argument");
+  if (!pbin && (!coef || ncoef < 1 || ncoef > 8))
+    return fail(BBT_EINVAL, "need phase bins or 1..8 polynomial coefficients");
+  if (n_phase < 1 || inner < 1 || (power && inner % 4))
+    return fail(BBT_EINVAL, "bad fold shape");
+  if (n <= 0 || n_bins <= 0) return BBT_OK;
+  if (n_bins > 65535) return fail(BBT_EUNSUPPORTED, "too many bins per call");
+  FoldArgs a{};
+  a.in = in;
+  a.sum = static_cast<float*>(sum);
+  a.count = static_cast<unsigned long long*>(count);
+  a.lo = reinterpret_cast<const long long*>(lo);
+  a.hi = reinterpret_cast<const long long*>(hi);
+  a.pbin = pbin;
+  a.inner = inner;
+  a.n = n;
+  a.i_first = i_first;
+  a.b_first = b_first;
+  a.i_ref = i_ref;
+  a.rate = rate;
+  a.ncoef = pbin ? 1 : ncoef;
+  for (int k = 0; k < 8; ++k) a.coef[k] = (!pbin && k < ncoef) ? coef[k] : 0.;
+  a.n_phase = n_phase;
+  const size_t smem = (size_t)n_phase * (inner + 1) * 4;
+  a.use_smem = smem <= 40 * 1024;
+  const int64_t chunks = std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div((int64_t)sm_count() * 8, n_bins),
+                           ceil_div(n, n_bins * 1024)));
+  dim3 grid((unsigned)chunks, (unsigned)n_bins);
+  if (power)
+    BBT_LAUNCH(fold_kernel<true>, grid, dim3(256), a.use_smem ? smem : 0,
+               as_stream(stream), a);
+  else
+    BBT_LAUNCH(fold_kernel<false>, grid, dim3(256), a.use_smem ? smem : 0,
+               as_stream(stream), a);
+  return check_launch("fold kernel");
+}
+
+int bbt_average_exec(const void* sum, const void* count, void* out,
+                     int64_t n_bins, int64_t inner, void* stream) {
+  if (!sum || !count || !out) return fail(BBT_EINVAL, "null argument");
+  if (n_bins <= 0 || inner <= 0) return BBT_OK;
+  BBT_LAUNCH(average_kernel, dim3(grid_for(n_bins * inner, 256)), dim3(256), 0,
+             as_stream(stream), static_cast<const float*>(sum),
+             static_cast<const unsigned long long*>(count),
+             static_cast<float*>(out), (long long)n_bins, (long long)inner);
+  return check_launch("average kernel");
+}
+
+
+}  // extern "C"

@@ -2,12 +2,14 @@
 //
 // Replaces the np.fft.{fft,ifft} calls the reference's NumpyFFTMaker makes
 // (baseband_tasks/fourier/numpy.py:33-49).  One FFT of N = 2^LOG2N points is
-// computed by T = N/E cooperating threads, each holding E (<=16) complex
-// values in registers.  Every radix-R stage (R <= 16) is a register-resident
-// butterfly; between stages the values are exchanged through a padded,
-// bank-conflict-free shared-memory buffer.  Thread t owns elements
-// t + T*e (e < E) both before and after the transform, so global loads and
-// stores of consecutive threads are coalesced and no bit-reversal pass exists.
+// computed by T = N/E cooperating threads, each holding E = 2^LOG2E (<= 32)
+// complex values in registers.  The transform is split into the fewest
+// radix-R stages with R <= E, as equal as possible; every stage is a
+// register-resident butterfly, and between stages the values are exchanged
+// through a padded, bank-conflict-free shared-memory buffer.  Thread t owns
+// elements t + T*e (e < E) both before and after the transform, so global
+// loads and stores of consecutive threads are coalesced and no bit-reversal
+// pass exists.
 //
 // The header is plain C++ so that the same code can be compiled by g++ in the
 // kernel-emulation test harness (tests/emu) as well as by nvcc.
@@ -132,55 +134,171 @@ struct Dft<16> {
   }
 };
 
-// ---------------------------------------------------------------------------
-// Configuration of a block FFT.
-constexpr int kLog2TwiddleTable = 13;  // largest single-pass FFT: 8192 points
-constexpr int kTwiddleTable = 1 << kLog2TwiddleTable;
-
-template <int LOG2N>
-struct FftCfg {
-  static constexpr int N = 1 << LOG2N;
-  static constexpr int LOG2E = LOG2N < 4 ? LOG2N : 4;
-  static constexpr int E = 1 << LOG2E;  // elements per thread
-  static constexpr int T = N / E;       // threads per FFT
-  static constexpr int NPAD = N + (N >> 4);  // exchange slots per FFT
-  // CTA shape: 256 threads (512 for the 8192-point transform), G FFTs per CTA.
-  static constexpr int THREADS = T > 256 ? T : 256;
-  static constexpr int G = THREADS / T;
-  static constexpr size_t SMEM_BYTES = (size_t)G * NPAD * sizeof(float) * 2;
+// 32 = 2 x 16: X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k].
+template <>
+struct Dft<32> {
+  static BBT_HD void run(cf* v) {
+    cf ev[16], od[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      ev[i] = v[2 * i];
+      od[i] = v[2 * i + 1];
+    }
+    Dft<16>::run(ev);
+    Dft<16>::run(od);
+    // cos, sin of k pi/16, k = 0..15.
+    const float c[16] = {1.f,
+                         0.98078528040323044913f,
+                         0.92387953251128675613f,
+                         0.83146961230254523708f,
+                         0.70710678118654752440f,
+                         0.55557023301960222474f,
+                         0.38268343236508977173f,
+                         0.19509032201612826785f,
+                         0.f,
+                         -0.19509032201612826785f,
+                         -0.38268343236508977173f,
+                         -0.55557023301960222474f,
+                         -0.70710678118654752440f,
+                         -0.83146961230254523708f,
+                         -0.92387953251128675613f,
+                         -0.98078528040323044913f};
+    const float s[16] = {0.f,
+                         0.19509032201612826785f,
+                         0.38268343236508977173f,
+                         0.55557023301960222474f,
+                         0.70710678118654752440f,
+                         0.83146961230254523708f,
+                         0.92387953251128675613f,
+                         0.98078528040323044913f,
+                         1.f,
+                         0.98078528040323044913f,
+                         0.92387953251128675613f,
+                         0.83146961230254523708f,
+                         0.70710678118654752440f,
+                         0.55557023301960222474f,
+                         0.38268343236508977173f,
+                         0.19509032201612826785f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      cf o;
+      if (k == 0)
+        o = od[0];
+      else if (k == 8)
+        o = mul_mi(od[8]);
+      else
+        o = cmul(od[k], mk(c[k], -s[k]));
+      v[k] = ev[k] + o;
+      v[k + 16] = ev[k] - o;
+    }
+  }
 };
 
-BBT_HD int padslot(int p) { return p + (p >> 4); }
+// ---------------------------------------------------------------------------
+// Twiddle table: exp(-2 pi i m / kTwiddleTable), m < kTwiddleTable; also the
+// largest single-CTA transform.
+constexpr int kLog2TwiddleTable = 14;
+constexpr int kTwiddleTable = 1 << kLog2TwiddleTable;
+
+// Split of a 2^LOG2N transform into the fewest stages of radix <= 2^LOG2E,
+// as equal as possible (larger radices first).
+template <int LOG2N, int LOG2E>
+struct StagePlan {
+  static constexpr int NS = LOG2N == 0 ? 0 : (LOG2N + LOG2E - 1) / LOG2E;
+  static BBT_HD constexpr int bits(int i) {
+    return NS == 0 ? 0 : LOG2N / NS + (i < LOG2N % NS ? 1 : 0);
+  }
+  static BBT_HD constexpr int before(int i) {  // log2 of points combined so far
+    int b = 0;
+    for (int s = 0; s < i; ++s) b += bits(s);
+    return b;
+  }
+};
+
+// Configuration of a block FFT: N points, E elements per thread, THREADS
+// threads per CTA, hence G = THREADS*E/N transforms ("lanes") per CTA.
+template <int LOG2N, int LOG2E_, int THREADS_>
+struct FftCfg {
+  static constexpr int LOG2E = LOG2E_ < LOG2N ? LOG2E_ : LOG2N;
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int E = 1 << LOG2E;  // elements per thread
+  static constexpr int T = N / E;       // threads per FFT
+  static constexpr int THREADS = THREADS_ > T ? THREADS_ : T;
+  static constexpr int G = THREADS / T;
+  using Plan = StagePlan<LOG2N, LOG2E>;
+  // Padding of the exchange buffer: one slot per 2^PADSHIFT, matched to the
+  // stride of the first stage's stores.
+  static constexpr int PADSHIFT = Plan::NS > 0 && Plan::bits(0) > 3
+                                      ? Plan::bits(0) : 4;
+  static constexpr int NPAD = N + (N >> PADSHIFT);  // exchange slots per FFT
+  static constexpr size_t SMEM_BYTES =
+      Plan::NS > 1 ? (size_t)G * NPAD * sizeof(float) * 2 : 16;
+};
 
 // Exchange-buffer addressing.  G FFTs ("lanes") share one CTA.
 //  LaneFast: consecutive threads work on consecutive lanes (column tiles);
 //  slot = padslot(p) * G + g.
 //  LaneSlow: consecutive threads work on consecutive elements of one FFT;
 //  slot = g * NPAD + padslot(p).
+template <int PADSHIFT>
 struct SmemLaneFast {
   cf* base;
   int g, G;
-  BBT_HD cf& at(int p) const { return base[padslot(p) * G + g]; }
+  BBT_HD cf& at(int p) const { return base[(p + (p >> PADSHIFT)) * G + g]; }
 };
-template <int NPAD>
+template <int PADSHIFT>
 struct SmemLaneSlow {
   cf* base;  // already offset to this lane
-  BBT_HD cf& at(int p) const { return base[padslot(p)]; }
+  BBT_HD cf& at(int p) const { return base[p + (p >> PADSHIFT)]; }
 };
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
 #define BBT_SYNC() __syncthreads()
-#define BBT_LDG(p) __ldg(p)
 #elif defined(BBT_EMULATE)
 }  // namespace bbt
 void bbt_emu_syncthreads();
 namespace bbt {
 #define BBT_SYNC() bbt_emu_syncthreads()
-#define BBT_LDG(p) (*(p))
 #else
 #define BBT_SYNC()
-#define BBT_LDG(p) (*(p))
 #endif
+
+// Streaming access to data that is touched once: do not let it displace the
+// twiddle tables in L1.
+BBT_HD cf ld_stream(const cf* p) {
+#if defined(__CUDA_ARCH__)
+  float2 w = __ldcs(reinterpret_cast<const float2*>(p));
+  return mk(w.x, w.y);
+#else
+  return *p;
+#endif
+}
+BBT_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+// v[e] <- v[e] * base * step^e (MODE 0), or conj(v[e] * base * step^e) * scale
+// (MODE 1), for e < 2^BITS, with pw[b] = step^(2^b): a linear phase ramp at
+// one complex multiply per element and per power.
+template <int BITS, int MODE>
+struct Ramp {
+  static BBT_HD void run(cf* v, cf w, const cf* pw, float scale) {
+    Ramp<BITS - 1, MODE>::run(v, w, pw, scale);
+    Ramp<BITS - 1, MODE>::run(v + (1 << (BITS - 1)), cmul(w, pw[BITS - 1]), pw,
+                              scale);
+  }
+};
+template <int MODE>
+struct Ramp<0, MODE> {
+  static BBT_HD void run(cf* v, cf w, const cf*, float scale) {
+    cf r = cmul(v[0], w);
+    v[0] = MODE ? mk(r.x * scale, -r.y * scale) : r;
+  }
+};
 
 BBT_HD cf ldtw(const cf* tw, int i) {
 #if defined(__CUDA_ARCH__)
@@ -191,15 +309,53 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 #endif
 }
 
+// b[r] *= w^r for r < R, with w = tw[kk]: powers of two are looked up, the
+// others are products of two looked-up or derived values.
+template <int R>
+BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
+  if constexpr (R >= 2) {
+    cf w[8];  // w^1 .. w^7
+    w[1] = ldtw(tw, kk);
+    if constexpr (R >= 4) {
+      w[2] = ldtw(tw, 2 * kk);
+      w[3] = cmul(w[2], w[1]);
+    }
+    if constexpr (R >= 8) {
+      w[4] = ldtw(tw, 4 * kk);
+      w[5] = cmul(w[4], w[1]);
+      w[6] = cmul(w[4], w[2]);
+      w[7] = cmul(w[4], w[3]);
+    }
+    constexpr int LOW = R < 8 ? R : 8;
+#pragma unroll
+    for (int r = 1; r < LOW; ++r) b[r] = cmul(b[r], w[r]);
+    if constexpr (R >= 16) {
+      cf hi = ldtw(tw, 8 * kk);
+      b[8] = cmul(b[8], hi);
+#pragma unroll
+      for (int r = 1; r < 8; ++r) b[8 + r] = cmul(b[8 + r], cmul(hi, w[r]));
+      if constexpr (R >= 32) {
+        cf hi2 = ldtw(tw, 16 * kk);
+        b[16] = cmul(b[16], hi2);
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          b[16 + r] = cmul(b[16 + r], cmul(hi2, w[r]));
+        cf hi3 = cmul(hi2, hi);
+        b[24] = cmul(b[24], hi3);
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          b[24 + r] = cmul(b[24 + r], cmul(hi3, w[r]));
+      }
+    }
+  }
+}
+
 // One Stockham stage: Ns = 2^LOG2NS points already combined, radix 2^LOG2R.
-// tw is the table exp(-2 pi i m / kTwiddleTable), m < kTwiddleTable.
-template <int LOG2N, int LOG2NS, int LOG2R, class Smem>
+template <class C, int LOG2NS, int LOG2R, class Smem>
 BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
-  using C = FftCfg<LOG2N>;
   constexpr int R = 1 << LOG2R;
   constexpr int Ns = 1 << LOG2NS;
   constexpr int NB = C::E / R;  // butterflies per thread
-  constexpr bool last = (LOG2NS + LOG2R == LOG2N);
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
     const int j = t + C::T * q;
@@ -207,29 +363,10 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
     cf b[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) b[r] = v[q + r * NB];
-    if constexpr (LOG2NS > 0) {
-      // w^r, w = exp(-2 pi i k / (Ns R)); table index k * TABLE / (Ns R).
-      const int kk = k << (kLog2TwiddleTable - LOG2NS - LOG2R);
-      cf w[R];
-      w[1] = ldtw(tw, kk);
-      if constexpr (R > 2) w[2] = ldtw(tw, 2 * kk);
-      if constexpr (R > 4) w[4] = ldtw(tw, 4 * kk);
-      if constexpr (R > 8) w[8] = ldtw(tw, 8 * kk);
-      if constexpr (R > 2) w[3] = cmul(w[2], w[1]);
-      if constexpr (R > 4) {
-        w[5] = cmul(w[4], w[1]);
-        w[6] = cmul(w[4], w[2]);
-        w[7] = cmul(w[4], w[3]);
-      }
-      if constexpr (R > 8) {
-#pragma unroll
-        for (int r = 9; r < 16; ++r) w[r] = cmul(w[8], w[r - 8]);
-      }
-#pragma unroll
-      for (int r = 1; r < R; ++r) b[r] = cmul(b[r], w[r]);
-    }
+    if constexpr (LOG2NS > 0)
+      apply_twiddles<R>(b, tw, k << (kLog2TwiddleTable - LOG2NS - LOG2R));
     Dft<R>::run(b);
-    if constexpr (last) {
+    if constexpr ((1 << (LOG2NS + LOG2R)) == C::N) {
 #pragma unroll
       for (int r = 0; r < R; ++r) v[q + r * NB] = b[r];
     } else {
@@ -238,7 +375,7 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
       for (int r = 0; r < R; ++r) sm.at(p0 + r * Ns) = b[r];
     }
   }
-  if constexpr (!last) {
+  if constexpr ((1 << (LOG2NS + LOG2R)) != C::N) {
     BBT_SYNC();
 #pragma unroll
     for (int e = 0; e < C::E; ++e) v[e] = sm.at(t + C::T * e);
@@ -246,27 +383,22 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
   }
 }
 
-template <int LOG2N, int LOG2NS, class Smem>
+template <class C, int STAGE, class Smem>
 struct FftStages {
   static BBT_HD void run(cf* v, int t, const cf* __restrict__ tw,
                          const Smem& sm) {
-    using C = FftCfg<LOG2N>;
-    constexpr int REM = LOG2N - LOG2NS;
-    constexpr int LR = REM < C::LOG2E ? REM : C::LOG2E;
-    fft_stage<LOG2N, LOG2NS, LR, Smem>(v, t, tw, sm);
-    FftStages<LOG2N, LOG2NS + LR, Smem>::run(v, t, tw, sm);
+    using P = typename C::Plan;
+    fft_stage<C, P::before(STAGE), P::bits(STAGE), Smem>(v, t, tw, sm);
+    if constexpr (STAGE + 1 < P::NS)
+      FftStages<C, STAGE + 1, Smem>::run(v, t, tw, sm);
   }
-};
-template <int LOG2N, class Smem>
-struct FftStages<LOG2N, LOG2N, Smem> {
-  static BBT_HD void run(cf*, int, const cf* __restrict__, const Smem&) {}
 };
 
 // Forward FFT of the N values spread over T threads (v[e] <-> t + T*e).
 // All threads of the CTA must call this together (it synchronises).
-template <int LOG2N, class Smem>
+template <class C, class Smem>
 BBT_HD void block_fft(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
-  FftStages<LOG2N, 0, Smem>::run(v, t, tw, sm);
+  if constexpr (C::Plan::NS > 0) FftStages<C, 0, Smem>::run(v, t, tw, sm);
 }
 
 }  // namespace bbt

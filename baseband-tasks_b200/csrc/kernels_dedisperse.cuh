@@ -10,7 +10,15 @@
 //                        the valid samples [pad_start+skip, pad_start+spf)
 // The spectrum is never brought into natural order: bin k = k1 + N1*k2 lives at
 // row k1, position k2, and the chirp is stored in that layout.
-// For N <= 8192 a single kernel (dd_small) does everything in one round trip.
+//
+// Layout of the work buffer between the passes (element (k1, n2, s)):
+//   interleaved  (k1*N2 + n2)*S + s   the input's own layout; pass 2 takes the
+//                                     S series of a row as the lanes of a tile
+//   planar       (k1*S + s)*N2 + n2   pass 1 de-interleaves on its stores, so
+//                                     pass 2 streams whole contiguous rows
+// chosen per plan so that every global access of every pass moves runs of at
+// least 64-128 contiguous bytes.
+// For N <= 16384 a single kernel (dd_small) does everything in one round trip.
 #pragma once
 #include "kernels_fft.cuh"
 
@@ -27,114 +35,264 @@ struct DdArgs {
   long long in_frame_stride, out_frame_stride;  // in complex elements
   long long N, S;       // frame length, interleaved series
   int log2n1, log2n2;
+  int planar;           // work-buffer layout
   long long lo, hi;     // valid flat range [(pad_start+skip)*S, (pad_start+spf)*S)
-  long long out_shift;  // pad_start*S
+  long long out_shift;  // (pad_start+skip)*S
   float scale;          // 1/N
+  int ahead;            // CTAs resident at a time: L2 prefetch distance
 };
 
-// Pass 1: forward column FFTs, frame -> work.
-template <int LOG2N1>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N1>::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
-  using C = FftCfg<LOG2N1>;
+// Ask L2 for `rows` runs of `run_bytes` each, `stride_bytes` apart: the tile a
+// CTA launched `ahead` blocks later will load, so that its DRAM fetch overlaps
+// this CTA's arithmetic.
+BBT_HD void prefetch_tile(const cf* base, long long rows, long long stride,
+                          int run_elems, int tid, int nthreads) {
+  const int lines = (run_elems * 8 + 127) / 128;
+  const long long total = rows * lines;
+  for (long long i = tid; i < total; i += nthreads) {
+    const long long r = i / lines;
+    const int l = (int)(i % lines);
+    prefetch_l2(base + r * stride + l * 16);
+  }
+}
+
+// Pass 1: forward column FFTs, frame -> work.  Lanes are consecutive flat
+// columns q = n2*S + s.
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
-  const long long cols = a.N / C::N * a.S;  // N2*S columns
+  const long long n2s = (a.N >> a.log2n1) * a.S;  // N2*S columns
   const int tid = threadIdx.x;
   const int g = tid % C::G, t = tid / C::G;
   const long long col = (long long)blockIdx.x * C::G + g;
   const long long frame = blockIdx.y;
-  const bool valid = col < cols;
+  const bool valid = col < n2s;
   const cf* src = a.in + frame * a.in_frame_stride + col;
-  cf* dst = a.work + frame * a.N * a.S + col;
   cf v[C::E];
 #pragma unroll
   for (int e = 0; e < C::E; ++e)
-    v[e] = valid ? src[(long long)(t + C::T * e) * cols] : mk(0.f, 0.f);
-  SmemLaneFast sm{smem, g, C::G};
-  block_fft<LOG2N1>(v, t, a.tw, sm);
+    v[e] = valid ? ld_stream(src + (long long)(t + C::T * e) * n2s)
+                 : mk(0.f, 0.f);
+  {
+    long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
+    if (nb >= gridDim.x) {
+      nb -= gridDim.x;
+      ++nf;
+    }
+    if (nf < gridDim.y && nb < gridDim.x) {
+      const long long c0 = nb * C::G;
+      const long long left = n2s - c0;
+      prefetch_tile(a.in + nf * a.in_frame_stride + c0, C::N, n2s,
+                    left < C::G ? (int)left : C::G, tid, C::THREADS);
+    }
+  }
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  block_fft<C>(v, t, a.tw, sm);
   if (valid) {
+    cf* dst = a.work + frame * a.N * a.S;
+    long long step;
+    if (a.planar) {
+      const long long n2 = col / a.S, s = col % a.S;
+      const long long N2 = a.N >> a.log2n1;
+      dst += s * N2 + n2;
+      step = a.S * N2;
+    } else {
+      dst += col;
+      step = n2s;
+    }
 #pragma unroll
-    for (int e = 0; e < C::E; ++e) dst[(long long)(t + C::T * e) * cols] = v[e];
+    for (int e = 0; e < C::E; ++e) dst[(long long)(t + C::T * e) * step] = v[e];
   }
 }
 
 // Pass 3: inverse column FFTs, work -> valid part of the output stream.
-template <int LOG2N1>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N1>::THREADS, 1) dd_col_inv_kernel(DdArgs a) {
-  using C = FftCfg<LOG2N1>;
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_inv_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
-  const long long cols = a.N / C::N * a.S;
+  const long long n2s = (a.N >> a.log2n1) * a.S;
   const int tid = threadIdx.x;
   const int g = tid % C::G, t = tid / C::G;
   const long long col = (long long)blockIdx.x * C::G + g;
   const long long frame = blockIdx.y;
-  const bool valid = col < cols;
-  const cf* src = a.work + frame * a.N * a.S + col;
-  cf* dst = a.out + frame * a.out_frame_stride - a.out_shift + col;
+  const bool valid = col < n2s;
+  const cf* src = a.work + frame * a.N * a.S;
+  long long step;
+  if (a.planar) {
+    const long long n2 = col / a.S, s = col % a.S;
+    const long long N2 = a.N >> a.log2n1;
+    src += s * N2 + n2;
+    step = a.S * N2;
+  } else {
+    src += col;
+    step = n2s;
+  }
   cf v[C::E];
 #pragma unroll
   for (int e = 0; e < C::E; ++e)
-    v[e] = valid ? cconj(src[(long long)(t + C::T * e) * cols]) : mk(0.f, 0.f);
-  SmemLaneFast sm{smem, g, C::G};
-  block_fft<LOG2N1>(v, t, a.tw, sm);
+    v[e] = valid ? cconj(ld_stream(src + (long long)(t + C::T * e) * step))
+                 : mk(0.f, 0.f);
+  {
+    long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
+    if (nb >= gridDim.x) {
+      nb -= gridDim.x;
+      ++nf;
+    }
+    if (nf < gridDim.y && nb < gridDim.x) {
+      const long long c0 = nb * C::G;
+      const cf* base = a.work + nf * a.N * a.S;
+      if (a.planar) {
+        // Runs of the tile's n2 values, one per (k1, s).
+        const long long N2 = a.N >> a.log2n1;
+        const long long n20 = c0 / a.S, s0 = c0 % a.S;
+        const int ns = a.S < C::G ? (int)a.S : C::G;       // series in tile
+        const int tn = a.S < C::G ? C::G / (int)a.S : 1;   // n2 per series
+        for (int si = 0; si < ns; ++si)
+          prefetch_tile(base + (s0 + si) * N2 + n20, C::N, a.S * N2, tn, tid,
+                        C::THREADS);
+      } else {
+        const long long left = n2s - c0;
+        prefetch_tile(base + c0, C::N, n2s, left < C::G ? (int)left : C::G,
+                      tid, C::THREADS);
+      }
+    }
+  }
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  block_fft<C>(v, t, a.tw, sm);
   if (valid) {
+    cf* dst = a.out + frame * a.out_frame_stride - a.out_shift;
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {
-      const long long flat = (long long)(t + C::T * e) * cols + col;
-      if (flat >= a.lo && flat < a.hi) dst[flat - col] = cconj(v[e]);
+      const long long flat = (long long)(t + C::T * e) * n2s + col;
+      if (flat >= a.lo && flat < a.hi) dst[flat] = cconj(v[e]);
     }
   }
 }
 
-// Pass 2: one CTA per G rows of one series.  Lanes are rows (k1), threads of a
-// lane walk along n2 with stride S.
-template <int LOG2N2>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N2>::THREADS, 1) dd_row_kernel(DdArgs a) {
-  using C = FftCfg<LOG2N2>;
+// Pass 2 on one row per lane.  PLANAR: lanes are G consecutive rows
+// rho = k1*S + s of the planar work buffer, threads of a lane walk along the
+// contiguous row.  Otherwise lanes are the series of one row (or of several
+// rows when S < G) of the interleaved buffer, consecutive threads taking
+// consecutive series.
+template <class C, bool PLANAR>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
-  const long long n1 = a.N >> LOG2N2;
+  const long long n1 = a.N >> a.log2n2;
   const int tid = threadIdx.x;
-  const int t = tid % C::T, g = tid / C::T;
-  const long long k1 = (long long)blockIdx.x * C::G + g;
-  const long long s = blockIdx.y;
-  const long long frame = blockIdx.z;
-  const bool valid = k1 < n1;
-  cf* row = a.work + frame * a.N * a.S + k1 * C::N * a.S + s;
-  const cf* chirp = a.chirp + ((long long)a.series_map[s] * n1 + k1) * C::N;
-  SmemLaneSlow<C::NPAD> sm{smem + (size_t)g * C::NPAD};
-  cf v[C::E], w[C::E];
+  const long long frame = blockIdx.y;
+  int t, g;
+  long long k1, s, stride;
+  bool valid;
+  cf* row = a.work + frame * a.N * a.S;
+  if (PLANAR) {
+    t = tid % C::T;
+    g = tid / C::T;
+    const long long rho = (long long)blockIdx.x * C::G + g;
+    valid = rho < n1 * a.S;
+    k1 = rho / a.S;
+    s = rho % a.S;
+    row += rho * C::N;
+    stride = 1;
+  } else {
+    g = tid % C::G;
+    t = tid / C::G;
+    // Series per CTA chunk, rows per CTA.
+    const int sc = a.S < C::G ? (int)a.S : C::G;
+    const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
+    const long long chunks = (a.S + sc - 1) / sc;
+    const long long rblk = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int kl = g / sc, sl = g % sc;
+    k1 = rblk * rpc + kl;
+    s = chunk * sc + sl;
+    valid = kl < rpc && k1 < n1 && s < a.S;
+    row += k1 * C::N * a.S + s;
+    stride = a.S;
+  }
+  const cf* chirp = a.chirp;
+  if (valid) chirp += ((long long)a.series_map[s] * n1 + k1) * C::N;
+  // Twiddle W_N^{k1 n2}, n2 = t + T e, as base * step^e.
+  cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
+  cf base = mk(1.f, 0.f);
+  if (valid) {
+    base = a.big.get(k1 * t);
+    pw[0] = a.big.get(k1 * C::T);
+#pragma unroll
+    for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
+    if ((t & 15) == 0) {
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) prefetch_l2(chirp + t + C::T * e);
+    }
+  }
+  cf v[C::E];
 #pragma unroll
   for (int e = 0; e < C::E; ++e) {
     const int n2 = t + C::T * e;
-    if (valid) {
-      w[e] = a.big.get(k1 * n2);
-      v[e] = cmul(row[(long long)n2 * a.S], w[e]);
-    } else {
-      w[e] = mk(1.f, 0.f);
-      v[e] = mk(0.f, 0.f);
+    v[e] = valid ? ld_stream(row + (long long)n2 * stride) : mk(0.f, 0.f);
+  }
+  {
+    // The rows the CTA `ahead` blocks later will load.
+    long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
+    if (nb >= gridDim.x) {
+      nb -= gridDim.x;
+      ++nf;
+    }
+    if (nf < gridDim.y && nb < gridDim.x) {
+      const cf* base2 = a.work + nf * a.N * a.S;
+      long long elems = (long long)C::G * C::N;
+      if (PLANAR) {
+        base2 += nb * C::G * C::N;
+      } else {
+        const int sc = a.S < C::G ? (int)a.S : C::G;
+        const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
+        const long long chunks = (a.S + sc - 1) / sc;
+        if (chunks == 1) {
+          base2 += (nb * rpc) * C::N * a.S;
+          elems = (long long)rpc * C::N * a.S;
+        } else {
+          elems = 0;  // strided chunks: leave to the hardware
+        }
+      }
+      const long long limit = a.N * a.S - (base2 - (a.work + nf * a.N * a.S));
+      if (elems > limit) elems = limit;
+      for (long long i = (long long)tid * 16; i < elems;
+           i += (long long)C::THREADS * 16)
+        prefetch_l2(base2 + i);
     }
   }
-  block_fft<LOG2N2>(v, t, a.tw, sm);
-  if (valid) {
-#pragma unroll
-    for (int e = 0; e < C::E; ++e)
-      v[e] = cconj(cmul(v[e], ldtw(chirp, t + C::T * e)));
+  if (valid) Ramp<C::LOG2E, 0>::run(v, base, pw, 1.f);
+  if (PLANAR) {
+    SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
+    block_fft<C>(v, t, a.tw, sm);
+  } else {
+    SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+    block_fft<C>(v, t, a.tw, sm);
   }
-  block_fft<LOG2N2>(v, t, a.tw, sm);
   if (valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
-      // conj(fft(conj(Y))) * conj(w) / N = conj(fft(conj(Y)) * w) / N
-      row[(long long)(t + C::T * e) * a.S] =
-          cscale(cconj(cmul(v[e], w[e])), a.scale);
+      v[e] = cconj(cmul(v[e], ld_stream(chirp + t + C::T * e)));
+  }
+  if (PLANAR) {
+    SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
+    block_fft<C>(v, t, a.tw, sm);
+  } else {
+    SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+    block_fft<C>(v, t, a.tw, sm);
+  }
+  if (valid) {
+    // conj(fft(conj(Y))) * conj(w) / N = conj(fft(conj(Y)) * w) / N
+    Ramp<C::LOG2E, 1>::run(v, base, pw, a.scale);
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      row[(long long)(t + C::T * e) * stride] = v[e];
   }
 }
 
-// Single pass for N <= 8192: lanes are (frame, series) pairs, series fastest.
+// Single pass for N <= 16384: lanes are (frame, series) pairs, series fastest.
 // LANEFAST (S > 1): consecutive threads take consecutive series; otherwise
 // consecutive threads walk along time.
-template <int LOG2N, bool LANEFAST>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) dd_small_kernel(DdArgs a, long long n_frames) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
+    dd_small_kernel(DdArgs a, long long n_frames) {
   cf* smem = BBT_SMEM(cf);
   const int tid = threadIdx.x;
   const int g = LANEFAST ? tid % C::G : tid / C::T;
@@ -146,18 +304,17 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) dd_small_kernel(DdA
   cf* dst = a.out + frame * a.out_frame_stride - a.out_shift + s;
   const cf* chirp = a.chirp;
   if (valid) chirp += (long long)a.series_map[s] * C::N;
-  LaneMap<LOG2N, LANEFAST> m(t, g);
   cf v[C::E];
 #pragma unroll
   for (int e = 0; e < C::E; ++e)
     v[e] = valid ? src[(long long)(t + C::T * e) * a.S] : mk(0.f, 0.f);
-  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  lane_fft<C, LANEFAST>(v, t, g, a.tw, smem);
   if (valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
       v[e] = cconj(cmul(v[e], ldtw(chirp, t + C::T * e)));
   }
-  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  lane_fft<C, LANEFAST>(v, t, g, a.tw, smem);
   if (valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {

@@ -73,9 +73,8 @@ struct ChanPowArgs {
   long long msub;         // concurrent spectrum sub-streams per bin
 };
 
-template <int LOG2N, bool LANEFAST, bool INTEGRATE>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST, bool INTEGRATE>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
   cf* smem = BBT_SMEM(cf);
   cf* smem1 = smem + (size_t)C::G * C::NPAD;
   const int tid = threadIdx.x;
@@ -123,14 +122,14 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) chanpow_kernel(Chan
       }
     }
     if (LANEFAST) {
-      SmemLaneFast s0{smem, g, C::G}, s1{smem1, g, C::G};
-      block_fft<LOG2N>(v0, t, a.tw, s0);
-      block_fft<LOG2N>(v1, t, a.tw, s1);
+      SmemLaneFast<C::PADSHIFT> s0{smem, g, C::G}, s1{smem1, g, C::G};
+      block_fft<C>(v0, t, a.tw, s0);
+      block_fft<C>(v1, t, a.tw, s1);
     } else {
-      SmemLaneSlow<C::NPAD> s0{smem + (size_t)g * C::NPAD},
+      SmemLaneSlow<C::PADSHIFT> s0{smem + (size_t)g * C::NPAD},
           s1{smem1 + (size_t)g * C::NPAD};
-      block_fft<LOG2N>(v0, t, a.tw, s0);
-      block_fft<LOG2N>(v1, t, a.tw, s1);
+      block_fft<C>(v0, t, a.tw, s0);
+      block_fft<C>(v1, t, a.tw, s1);
     }
     if (valid) {
 #pragma unroll

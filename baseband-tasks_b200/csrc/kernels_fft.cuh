@@ -26,13 +26,11 @@ struct FftArgs {
   float scale;      // applied to the output
 };
 
-template <int LOG2N, bool LANEFAST>
+template <class C, bool LANEFAST>
 struct LaneMap {
-  using C = FftCfg<LOG2N>;
   int t, g;
   long long b, c;  // outer index, inner column
   bool valid;
-  BBT_HD LaneMap(int t_, int g_) : t(t_), g(g_), b(0), c(0), valid(true) {}
   BBT_HD LaneMap(int tid, long long blk, const FftArgs& a) {
     if (LANEFAST) {
       // Lanes enumerate (outer, inner) pairs with the inner column fastest.
@@ -52,26 +50,32 @@ struct LaneMap {
   }
 };
 
-template <int LOG2N, bool LANEFAST>
-BBT_HD void lane_fft(cf* v, const LaneMap<LOG2N, LANEFAST>& m, const cf* tw,
-                     cf* smem) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST>
+BBT_HD void lane_fft(cf* v, int t, int g, const cf* tw, cf* smem) {
   if (LANEFAST) {
-    SmemLaneFast sm{smem, m.g, C::G};
-    block_fft<LOG2N>(v, m.t, tw, sm);
+    SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+    block_fft<C>(v, t, tw, sm);
   } else {
-    SmemLaneSlow<C::NPAD> sm{smem + (size_t)m.g * C::NPAD};
-    block_fft<LOG2N>(v, m.t, tw, sm);
+    SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
+    block_fft<C>(v, t, tw, sm);
   }
 }
 
+// Default shape of a block FFT of 2^LOG2N points: elements per thread and
+// threads per CTA.
+template <int LOG2N>
+struct DefaultCfg {
+  static constexpr int LOG2E = LOG2N <= 4 ? LOG2N : (LOG2N <= 8 ? 4 : 5);
+  static constexpr int THREADS = LOG2N >= 14 ? 512 : 256;
+  using type = FftCfg<LOG2N, LOG2E, THREADS>;
+};
+
 // Complex to complex.
-template <int LOG2N, bool LANEFAST>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2c_kernel(FftArgs a) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) fft_c2c_kernel(FftArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long blk = blockIdx.x;
-  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  LaneMap<C, LANEFAST> m((int)threadIdx.x, blk, a);
   const cf* in = static_cast<const cf*>(a.in);
   cf* out = static_cast<cf*>(a.out);
   const long long base = m.b * C::N * a.inner + m.c;
@@ -82,7 +86,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2c_kernel(FftA
     if (m.valid) x = in[base + (long long)(m.t + C::T * e) * a.inner];
     v[e] = a.inverse ? cconj(x) : x;
   }
-  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  lane_fft<C, LANEFAST>(v, m.t, m.g, a.tw, smem);
   if (m.valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {
@@ -95,12 +99,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2c_kernel(FftA
 
 // Real to complex: n real samples -> n/2+1 bins (fourier/numpy.py:41-43).
 // First version: transform the real data as complex with zero imaginary part.
-template <int LOG2N, bool LANEFAST>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_r2c_kernel(FftArgs a) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) fft_r2c_kernel(FftArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long blk = blockIdx.x;
-  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  LaneMap<C, LANEFAST> m((int)threadIdx.x, blk, a);
   const float* in = static_cast<const float*>(a.in);
   cf* out = static_cast<cf*>(a.out);
   const long long ibase = m.b * C::N * a.inner + m.c;
@@ -112,7 +115,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_r2c_kernel(FftA
     if (m.valid) x = in[ibase + (long long)(m.t + C::T * e) * a.inner];
     v[e] = mk(x, 0.f);
   }
-  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  lane_fft<C, LANEFAST>(v, m.t, m.g, a.tw, smem);
   if (m.valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {
@@ -124,12 +127,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_r2c_kernel(FftA
 
 // Complex to real: n/2+1 bins -> n real samples (fourier/numpy.py:46-49).
 // Like numpy's irfft the imaginary parts of bins 0 and n/2 are ignored.
-template <int LOG2N, bool LANEFAST>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2r_kernel(FftArgs a) {
-  using C = FftCfg<LOG2N>;
+template <class C, bool LANEFAST>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) fft_c2r_kernel(FftArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long blk = blockIdx.x;
-  LaneMap<LOG2N, LANEFAST> m((int)threadIdx.x, blk, a);
+  LaneMap<C, LANEFAST> m((int)threadIdx.x, blk, a);
   const cf* in = static_cast<const cf*>(a.in);
   float* out = static_cast<float*>(a.out);
   const long long ibase = m.b * (C::N / 2 + 1) * a.inner + m.c;
@@ -150,7 +152,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(FftCfg<LOG2N>::THREADS, 1) fft_c2r_kernel(FftA
     }
     v[e] = x;
   }
-  lane_fft<LOG2N, LANEFAST>(v, m, a.tw, smem);
+  lane_fft<C, LANEFAST>(v, m.t, m.g, a.tw, smem);
   if (m.valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
@@ -183,8 +185,8 @@ BBT_GLOBAL void transpose_kernel(const cf* BBT_RESTRICT in, cf* BBT_RESTRICT out
 // conjugate).  Only used by the generic large-N FFTMaker path; the
 // dedispersion plan folds this into its row kernel.
 struct BigTwiddle {
-  const cf* lo;  // exp(-2 pi i m / N), m < 8192
-  const cf* hi;  // exp(-2 pi i m 8192 / N), m < N / 8192
+  const cf* lo;  // exp(-2 pi i m / N), m < kTwiddleTable
+  const cf* hi;  // exp(-2 pi i m kTwiddleTable / N), m < N / kTwiddleTable
   BBT_HD cf get(long long m) const {
     cf w = ldtw(lo, (int)(m & (kTwiddleTable - 1)));
     const long long h = m >> kLog2TwiddleTable;

@@ -86,7 +86,7 @@ inline int sm_count() { return 4; }
 #else
 // --------------------------------------------------------------------- CUDA
 #include <cuda_runtime.h>
-#define BBT_GLOBAL __global__
+#define BBT_GLOBAL static __global__
 #define BBT_DEV __device__ __forceinline__
 #define BBT_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define BBT_SMEM(type) reinterpret_cast<type*>(bbt_dyn_smem)

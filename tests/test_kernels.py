@@ -63,7 +63,7 @@ def run_fft(b, x, n, outer, inner, kind, direction, scale, out_shape,
         lib.bbt_fft_plan_destroy(plan)
 
 
-@pytest.mark.parametrize('log2n', list(range(1, 14)))
+@pytest.mark.parametrize('log2n', list(range(1, 15)))
 def test_fft_c2c_contiguous(backend, log2n):
     rng = np.random.default_rng(log2n)
     n = 1 << log2n
@@ -103,7 +103,7 @@ def test_fft_real(backend, log2n, inner):
     assert_voltage(back, np.fft.irfft(want, n=n, axis=1).astype('f4'))
 
 
-@pytest.mark.parametrize('log2n', [14, 15, 17])
+@pytest.mark.parametrize('log2n', [15, 16, 18])
 def test_fft_large(backend, log2n):
     if log2n > 15 and not backend.big:
         pytest.skip('too slow on host threads')
@@ -239,13 +239,19 @@ def test_dedisperse_small(backend, case):
         dd.close()
 
 
-@pytest.mark.parametrize('log2n,S,log2n1', [(14, 1, 0), (14, 2, 0),
-                                            (15, 3, 5), (16, 2, 3),
-                                            (20, 2, 0), (22, 2, 10)])
+INTER, E32, R16 = 512, 1024, 2048   # plan hints: layout, thread shapes
+
+
+@pytest.mark.parametrize('log2n,S,log2n1', [
+    (14, 1, 0), (14, 2, 0), (15, 3, 5), (16, 2, 3), (14, 2, 4 | INTER),
+    (13, 16, INTER), (15, 3, 5 | INTER | E32), (15, 1, 5 | E32),
+    (15, 1, 5 | R16), (14, 2, 4 | INTER | R16), (24, 2, R16),
+    (20, 2, 0), (20, 16, 0), (20, 16, INTER), (20, 16, 6 | E32),
+    (22, 2, 10), (24, 2, 0)])
 def test_dedisperse_large(backend, log2n, S, log2n1):
     if log2n > 16 and not backend.big:
         pytest.skip('too slow on host threads')
-    if backend.name == 'emu' and log2n > 14 and S > 2:
+    if backend.name == 'emu' and log2n > 14 and S > 2 and not (log2n1 & E32):
         pytest.skip('too slow on host threads')
     rng = np.random.default_rng(500 + log2n)
     N = 1 << log2n
@@ -255,9 +261,9 @@ def test_dedisperse_large(backend, log2n, S, log2n1):
     k = 1. / 2.41e-4
     width = (1. / (f0 - rate / 2) ** 2 - 1. / (f0 + rate / 2) ** 2) * k
     dm = (N / 5) / (rate * 1e6) / width
-    n_in = 2 * N + N // 3
+    n_in = 2 * N + N // 3 if log2n < 24 else N + N // 2
     shape = (S,) if S > 1 else ()
-    sb = np.array([1, -1, 1][:S]) if S > 1 else 1
+    sb = np.where(np.arange(S) % 2, -1, 1) if S > 1 else 1
     probe = orc.DispersePlan(dm, f0, sb, rate, True, n_in, 1, shape,
                              fast_len=orc.next_pow2, samples_per_frame=1)
     spf = N - probe.pad_start - probe.pad_end

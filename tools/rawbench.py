@@ -67,7 +67,7 @@ def sec_fft():
     total = 1 << 27   # complex points = 1 GiB
     x = torch.randn(total, dtype=torch.complex64, device=dev)
     y = torch.empty_like(x)
-    for log2n in (6, 8, 10, 11, 12, 13):
+    for log2n in (6, 8, 10, 11, 12, 13, 14):
         n = 1 << log2n
         plan = ctypes.c_void_p()
         lib.check(lib.bbt_fft_plan_create(ctypes.byref(plan), n, total // n,
@@ -120,23 +120,27 @@ def dd_plan(N, S, pad_start, n_valid, log2n1):
 
 
 def sec_dd():
-    for (N, S, frames, hints) in ((1 << 20, 16, 4, (0, 6, 7, 8, 9, 10)),
-                                  (1 << 24, 2, 2, (0, 11, 12, 13)),
-                                  (1 << 14, 2050, 2, (0,)),
-                                  (1 << 13, 2050, 4, (0,))):
+    # planar, interleaved, E=32 column FFTs, 16-element row FFTs
+    P, I, E, R = 256, 512, 1024, 2048
+    for (N, S, frames, hints) in (
+            (1 << 20, 16, 4, (I, I | R, 0, R, 7 | P, 7 | P | R, 9 | I)),
+            (1 << 24, 2, 2, (0, R, 11 | P, 11 | P | R)),
+            (1 << 22, 2, 4, (0, R, 9 | P, 9 | P | R)),
+            (1 << 14, 2050, 2, (0,)),
+            (1 << 13, 2050, 4, (0,))):
         pad = N // 5
         spf = N - pad
         n_in = spf * (frames - 1) + N
         x = torch.randn(n_in * S, dtype=torch.complex64, device=dev)
         out = torch.empty(spf * frames * S, dtype=torch.complex64, device=dev)
         for h in hints:
-            if N <= 8192 and h:
+            if N <= 16384 and h:
                 continue
             plan = dd_plan(N, S, pad // 2, spf, h)
             wb = lib.bbt_dedisperse_work_bytes(plan, frames)
             work = torch.empty(max(wb, 8) // 8, dtype=torch.complex64,
                                device=dev)
-            passes = 3 if N > 8192 else 1
+            passes = 3 if (N > 16384 or (S > 1 and N > 1024)) else 1
             report(f'dedisperse N=2^{int(np.log2(N))} S={S} frames={frames} '
                    f'log2n1={h}',
                    timeit(lambda: lib.check(lib.bbt_dedisperse_exec(
@@ -182,7 +186,7 @@ def sec_chan():
                    ptr(c), stream()))), x.numel() * 8)
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     secs = sys.argv[1:] or ['copy', 'fft', 'dd', 'chan']
     print(torch.cuda.get_device_name(0), flush=True)
     for s in secs:
