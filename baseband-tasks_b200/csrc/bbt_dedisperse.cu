@@ -53,7 +53,7 @@ int launch_dd_col(bool inverse, const DdArgs& a, int64_t n_frames,
 template <int L2, bool PLANAR, bool ROW16>
 int launch_dd_row(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
   using C = FftCfg<L2, ROW16 ? 4 : 5,
-                   ROW16 ? 1024 : ((PLANAR && L2 < 14) ? 256 : 512)>;
+                   ROW16 ? 1024 : 512>;
   const int64_t n1 = a.N >> L2;
   int64_t blocks;
   if (PLANAR) {

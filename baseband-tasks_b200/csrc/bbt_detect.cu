@@ -4,7 +4,16 @@
 
 using namespace bbt;
 
+namespace {
+int g_chan_variant = 0;  // bbt_tune(1, v): tile shape of the 1024-channelizer
+}
+
 extern "C" {
+
+int bbt_tune(int key, int value) {
+  if (key == 1) g_chan_variant = value;
+  return BBT_OK;
+}
 
 // ----------------------------------------------------------------- detection
 int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
@@ -29,17 +38,56 @@ int bbt_square_exec(const void* in, void* out, int64_t n, int is_complex,
 
 }  // extern "C"
 namespace {
-// Two transforms (both polarizations) live in each thread: 16 elements each.
+// Shape of the channelizer tiles: 2^LOG2E values per thread; enough threads
+// for 8 lanes (runs of 64 bytes per time sample) where the transform allows.
 template <int L>
-using ChanCfg = FftCfg<L, (L < 4 ? L : 4), 256>;
+struct ChanCfg {
+  static constexpr int LOG2E = L < 4 ? L : (L == 14 ? 5 : 4);
+  static constexpr int T = (1 << L) >> LOG2E;
+  static constexpr int THREADS = T * 8 > 256 ? (T * 8 > 1024 ? 1024 : T * 8)
+                                             : 256;
+  using type = FftCfg<L, LOG2E, THREADS>;
+};
 
-template <int L, bool LANEFAST, bool INTEGRATE>
-int launch_chanpow(const ChanPowArgs& a, int64_t n_bins, bbt_stream_t st) {
-  using C = ChanCfg<L>;
-  const int64_t blocks = ceil_div(a.msub * a.M, C::G);
+template <class C, bool INTEGRATE>
+int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
+                       bbt_stream_t st);
+
+template <int L, bool INTEGRATE>
+int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
+                   bbt_stream_t st) {
+  if constexpr (L == 10) {
+    if (g_chan_variant == 1)
+      return launch_chanpow_cfg<FftCfg<10, 3, 1024>, INTEGRATE>(a, n_bins,
+                                                                max_width, st);
+    if (g_chan_variant == 2)
+      return launch_chanpow_cfg<FftCfg<10, 4, 256>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
+    if (g_chan_variant == 3)
+      return launch_chanpow_cfg<FftCfg<10, 3, 512>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
+    if (g_chan_variant == 0 || g_chan_variant == 4)
+      return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
+  }
+  return launch_chanpow_cfg<typename ChanCfg<L>::type, INTEGRATE>(
+      a, n_bins, max_width, st);
+}
+
+template <class C, bool INTEGRATE>
+int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
+                       bbt_stream_t st) {
+  constexpr int64_t units = C::G / 2;  // (sub-stream, m) pairs per CTA
+  // Sub-streams per bin so that the grid fills the GPU a few times over.
+  const int64_t want = (int64_t)sm_count() * 4 * units;
+  int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));
+  if (msub > max_width) msub = max_width;
+  if (msub < 1) msub = 1;
+  a.msub = msub;
+  const int64_t blocks = ceil_div(msub * a.M, units);
   dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
-  const size_t smem = 2 * C::SMEM_BYTES;
-  auto kern = chanpow_kernel<C, LANEFAST, INTEGRATE>;
+  const size_t smem = C::SMEM_BYTES;
+  auto kern = chanpow_kernel<C, INTEGRATE>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
   prof_next_name = INTEGRATE ? "chanpow_integrate" : "chanpow";
@@ -51,18 +99,7 @@ template <bool INTEGRATE>
 int run_chanpow(int log2n, ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                 bbt_stream_t st) {
   int rc = BBT_EUNSUPPORTED;
-  const bool lanefast = a.M > 1;
-#define F(L)                                                                 \
-  {                                                                          \
-    const int64_t g = ChanCfg<L>::G;                                          \
-    const int64_t want = (int64_t)sm_count() * 8 * g;                        \
-    int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));           \
-    if (msub > max_width) msub = max_width;                                  \
-    if (msub < 1) msub = 1;                                                  \
-    a.msub = msub;                                                           \
-    rc = lanefast ? launch_chanpow<L, true, INTEGRATE>(a, n_bins, st)        \
-                  : launch_chanpow<L, false, INTEGRATE>(a, n_bins, st);      \
-  }
+#define F(L) rc = launch_chanpow<L, INTEGRATE>(a, n_bins, max_width, st)
   BBT_FOR_LOG2(log2n, F)
 #undef F
   if (rc == BBT_EUNSUPPORTED)

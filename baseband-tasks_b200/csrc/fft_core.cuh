@@ -240,16 +240,23 @@ struct FftCfg {
 //  slot = padslot(p) * G + g.
 //  LaneSlow: consecutive threads work on consecutive elements of one FFT;
 //  slot = g * NPAD + padslot(p).
+// ``slot(p)`` is the padded position of element p; ``ref(s)`` the storage
+// of padded position s.  Offsets between the elements a thread touches in one
+// stage are compile-time constants in padded positions (see fft_stage).
 template <int PADSHIFT>
 struct SmemLaneFast {
   cf* base;
   int g, G;
-  BBT_HD cf& at(int p) const { return base[(p + (p >> PADSHIFT)) * G + g]; }
+  static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
+  BBT_HD cf& ref(int s) const { return base[s * G + g]; }
+  BBT_HD cf& at(int p) const { return ref(slot(p)); }
 };
 template <int PADSHIFT>
 struct SmemLaneSlow {
   cf* base;  // already offset to this lane
-  BBT_HD cf& at(int p) const { return base[p + (p >> PADSHIFT)]; }
+  static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
+  BBT_HD cf& ref(int s) const { return base[s]; }
+  BBT_HD cf& at(int p) const { return ref(slot(p)); }
 };
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
@@ -370,15 +377,36 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
 #pragma unroll
       for (int r = 0; r < R; ++r) v[q + r * NB] = b[r];
     } else {
+      constexpr int PADN = 1 << C::PADSHIFT;
       const int p0 = ((j - k) << LOG2R) + k;
+      if constexpr (Ns % PADN == 0) {
+        // (p0 + r Ns) >> PADSHIFT = (p0 >> PADSHIFT) + r (Ns >> PADSHIFT).
+        const int s0 = Smem::slot(p0);
 #pragma unroll
-      for (int r = 0; r < R; ++r) sm.at(p0 + r * Ns) = b[r];
+        for (int r = 0; r < R; ++r) sm.ref(s0 + r * (Ns + Ns / PADN)) = b[r];
+      } else if constexpr (R * Ns <= PADN) {
+        // All R outputs fall in one padding block.
+        const int s0 = Smem::slot(p0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm.ref(s0 + r * Ns) = b[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm.at(p0 + r * Ns) = b[r];
+      }
     }
   }
   if constexpr ((1 << (LOG2NS + LOG2R)) != C::N) {
+    constexpr int PADN = 1 << C::PADSHIFT;
     BBT_SYNC();
+    if constexpr (C::T % PADN == 0) {
+      const int s0 = Smem::slot(t);
 #pragma unroll
-    for (int e = 0; e < C::E; ++e) v[e] = sm.at(t + C::T * e);
+      for (int e = 0; e < C::E; ++e)
+        v[e] = sm.ref(s0 + e * (C::T + C::T / PADN));
+    } else {
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) v[e] = sm.at(t + C::T * e);
+    }
     BBT_SYNC();
   }
 }

@@ -69,10 +69,16 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
   const bool valid = col < n2s;
   const cf* src = a.in + frame * a.in_frame_stride + col;
   cf v[C::E];
+  {
+    // Walk down the column: one 64-bit add per element.
+    const cf* pe = src + (long long)t * n2s;
+    const long long pstep = (long long)C::T * n2s;
 #pragma unroll
-  for (int e = 0; e < C::E; ++e)
-    v[e] = valid ? ld_stream(src + (long long)(t + C::T * e) * n2s)
-                 : mk(0.f, 0.f);
+    for (int e = 0; e < C::E; ++e) {
+      v[e] = valid ? ld_stream(pe) : mk(0.f, 0.f);
+      pe += pstep;
+    }
+  }
   {
     long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
     if (nb >= gridDim.x) {
@@ -100,8 +106,13 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
       dst += col;
       step = n2s;
     }
+    dst += (long long)t * step;
+    const long long pstep = (long long)C::T * step;
 #pragma unroll
-    for (int e = 0; e < C::E; ++e) dst[(long long)(t + C::T * e) * step] = v[e];
+    for (int e = 0; e < C::E; ++e) {
+      *dst = v[e];
+      dst += pstep;
+    }
   }
 }
 
@@ -127,10 +138,15 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_inv_kernel(DdArgs a) {
     step = n2s;
   }
   cf v[C::E];
+  {
+    const cf* pe = src + (long long)t * step;
+    const long long pstep = (long long)C::T * step;
 #pragma unroll
-  for (int e = 0; e < C::E; ++e)
-    v[e] = valid ? cconj(ld_stream(src + (long long)(t + C::T * e) * step))
-                 : mk(0.f, 0.f);
+    for (int e = 0; e < C::E; ++e) {
+      v[e] = valid ? cconj(ld_stream(pe)) : mk(0.f, 0.f);
+      pe += pstep;
+    }
+  }
   {
     long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
     if (nb >= gridDim.x) {
@@ -159,13 +175,30 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_inv_kernel(DdArgs a) {
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   block_fft<C>(v, t, a.tw, sm);
   if (valid) {
-    cf* dst = a.out + frame * a.out_frame_stride - a.out_shift;
+    long long flat = (long long)t * n2s + col;
+    const long long fstep = (long long)C::T * n2s;
+    cf* dst = a.out + frame * a.out_frame_stride - a.out_shift + flat;
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {
-      const long long flat = (long long)(t + C::T * e) * n2s + col;
-      if (flat >= a.lo && flat < a.hi) dst[flat] = cconj(v[e]);
+      if (flat >= a.lo && flat < a.hi) *dst = cconj(v[e]);
+      flat += fstep;
+      dst += fstep;
     }
   }
+}
+
+// Multiply the elements n2 = t + T e of row k1 by the twiddle W_N^{k1 n2}
+// (MODE 0) or by its conjugate and the scale (MODE 1: v <- conj(v w) scale),
+// generated as base * step^e from two table look-ups.  Called before and
+// after the transforms rather than keeping the powers in registers.
+template <class C, int MODE>
+BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
+  cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
+  const cf base = big.get((long long)k1 * t);
+  pw[0] = big.get((long long)k1 * C::T);
+#pragma unroll
+  for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
+  Ramp<C::LOG2E, MODE>::run(v, base, pw, scale);
 }
 
 // Pass 2 on one row per lane.  PLANAR: lanes are G consecutive rows
@@ -209,25 +242,18 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_kernel(DdArgs a) {
   }
   const cf* chirp = a.chirp;
   if (valid) chirp += ((long long)a.series_map[s] * n1 + k1) * C::N;
-  // Twiddle W_N^{k1 n2}, n2 = t + T e, as base * step^e.
-  cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
-  cf base = mk(1.f, 0.f);
-  if (valid) {
-    base = a.big.get(k1 * t);
-    pw[0] = a.big.get(k1 * C::T);
+  if (valid && (t & 15) == 0) {
 #pragma unroll
-    for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
-    if ((t & 15) == 0) {
-#pragma unroll
-      for (int e = 0; e < C::E; ++e) prefetch_l2(chirp + t + C::T * e);
-    }
+    for (int e = 0; e < C::E; ++e) prefetch_l2(chirp + t + C::T * e);
   }
   cf v[C::E];
+  // Offsets within a row tile fit in 32 bits: independent address per element.
+  const unsigned ustride = (unsigned)stride;
+  const unsigned off0 = (unsigned)t * ustride;
 #pragma unroll
-  for (int e = 0; e < C::E; ++e) {
-    const int n2 = t + C::T * e;
-    v[e] = valid ? ld_stream(row + (long long)n2 * stride) : mk(0.f, 0.f);
-  }
+  for (int e = 0; e < C::E; ++e)
+    v[e] = valid ? ld_stream(row + (off0 + (unsigned)(C::T * e) * ustride))
+                 : mk(0.f, 0.f);
   {
     // The rows the CTA `ahead` blocks later will load.
     long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
@@ -258,7 +284,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_kernel(DdArgs a) {
         prefetch_l2(base2 + i);
     }
   }
-  if (valid) Ramp<C::LOG2E, 0>::run(v, base, pw, 1.f);
+  if (valid) row_ramp<C, 0>(v, a.big, (int)k1, t, 1.f);
   if (PLANAR) {
     SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
     block_fft<C>(v, t, a.tw, sm);
@@ -280,10 +306,10 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_kernel(DdArgs a) {
   }
   if (valid) {
     // conj(fft(conj(Y))) * conj(w) / N = conj(fft(conj(Y)) * w) / N
-    Ramp<C::LOG2E, 1>::run(v, base, pw, a.scale);
+    row_ramp<C, 1>(v, a.big, (int)k1, t, a.scale);
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
-      row[(long long)(t + C::T * e) * stride] = v[e];
+      row[off0 + (unsigned)(C::T * e) * ustride] = v[e];
   }
 }
 

@@ -73,21 +73,21 @@ struct ChanPowArgs {
   long long msub;         // concurrent spectrum sub-streams per bin
 };
 
-template <class C, bool LANEFAST, bool INTEGRATE>
+// Lanes of a tile are (unit, polarization) pairs, polarization fastest, where
+// a unit is one (spectrum sub-stream, m) pair with m fastest; consecutive
+// threads take consecutive lanes, so a warp reads runs of G*8 contiguous
+// bytes per time sample.  After the transform the two threads holding X and Y
+// of a channel swap half of their values (one shuffle per value), and each
+// forms all four products for every other channel.
+template <class C, bool INTEGRATE>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
+  static_assert(C::G % 2 == 0 && C::E % 2 == 0, "pairs of lanes and values");
   cf* smem = BBT_SMEM(cf);
-  cf* smem1 = smem + (size_t)C::G * C::NPAD;
   const int tid = threadIdx.x;
-  int t, g;
-  if (LANEFAST) {
-    g = tid % C::G;
-    t = tid / C::G;
-  } else {
-    t = tid % C::T;
-    g = tid / C::T;
-  }
-  const long long lane = (long long)blockIdx.x * C::G + g;
-  const long long m = lane % a.M, jsub = lane / a.M;
+  const int g = tid % C::G, t = tid / C::G;
+  const int p = g & 1;
+  const long long unit = (long long)blockIdx.x * (C::G / 2) + (g >> 1);
+  const long long m = unit % a.M, jsub = unit / a.M;
   long long lo, hi;  // spectra (relative to j_first) this CTA walks through
   long long b = 0;
   if (INTEGRATE) {
@@ -101,62 +101,69 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
     hi = a.n_spec;
   }
   const bool lane_ok = jsub < a.msub;
-  f4 acc[C::E];
+  const cf* in = reinterpret_cast<const cf*>(a.in);
+  const long long row = a.M * 2;  // complex values per time sample
+  f4 acc[C::E / 2];
   if (INTEGRATE) {
 #pragma unroll
-    for (int e = 0; e < C::E; ++e) acc[e].x = acc[e].y = acc[e].z = acc[e].w = 0.f;
+    for (int i = 0; i < C::E / 2; ++i)
+      acc[i].x = acc[i].y = acc[i].z = acc[i].w = 0.f;
   }
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   for (long long j0 = lo; j0 < hi; j0 += a.msub) {
     const long long j = j0 + jsub;
     const bool valid = lane_ok && j < hi;
-    const cf2* src = a.in + (j * C::N) * a.M + m;
-    cf v0[C::E], v1[C::E];
-#pragma unroll
-    for (int e = 0; e < C::E; ++e) {
-      if (valid) {
-        const cf2 x = src[(long long)(t + C::T * e) * a.M];
-        v0[e] = x.a;
-        v1[e] = x.b;
-      } else {
-        v0[e] = v1[e] = mk(0.f, 0.f);
-      }
-    }
-    if (LANEFAST) {
-      SmemLaneFast<C::PADSHIFT> s0{smem, g, C::G}, s1{smem1, g, C::G};
-      block_fft<C>(v0, t, a.tw, s0);
-      block_fft<C>(v1, t, a.tw, s1);
-    } else {
-      SmemLaneSlow<C::PADSHIFT> s0{smem + (size_t)g * C::NPAD},
-          s1{smem1 + (size_t)g * C::NPAD};
-      block_fft<C>(v0, t, a.tw, s0);
-      block_fft<C>(v1, t, a.tw, s1);
-    }
-    if (valid) {
+    const cf* src = in + (j * C::N) * row + m * 2 + p;
+    cf v[C::E];
+    const long long pstep = (long long)C::T * row;
+    {
+      const cf* pe = src + (long long)t * row;
 #pragma unroll
       for (int e = 0; e < C::E; ++e) {
-        const f4 p = stokes_like(v0[e], v1[e]);
-        if (INTEGRATE) {
-          acc[e].x += p.x;
-          acc[e].y += p.y;
-          acc[e].z += p.z;
-          acc[e].w += p.w;
-        } else {
-          f4* o = reinterpret_cast<f4*>(a.out) +
-                  ((j * C::N + (t + C::T * e)) * a.M + m);
-          *o = p;
-        }
+        v[e] = valid ? ld_stream(pe) : mk(0.f, 0.f);
+        pe += pstep;
+      }
+    }
+    if (lane_ok && j + a.msub < hi && (g & 15) == 0) {
+      // Next spectrum of this lane group into L2 while this one is transformed.
+      const cf* pe = src + a.msub * C::N * row + (long long)t * row;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        prefetch_l2(pe);
+        pe += pstep;
+      }
+    }
+    block_fft<C>(v, t, a.tw, sm);
+#pragma unroll
+    for (int i = 0; i < C::E / 2; ++i) {
+      // Keep value 2i+p, swap value 2i+(1-p) for the partner's 2i+p.
+      const cf mine = p ? v[2 * i + 1] : v[2 * i];
+      const cf send = p ? v[2 * i] : v[2 * i + 1];
+      cf other;
+      other.x = shfl_xor1(send.x);
+      other.y = shfl_xor1(send.y);
+      const f4 q = p ? stokes_like(other, mine) : stokes_like(mine, other);
+      if (INTEGRATE) {
+        acc[i].x += q.x;
+        acc[i].y += q.y;
+        acc[i].z += q.z;
+        acc[i].w += q.w;
+      } else if (valid) {
+        const int k = t + C::T * (2 * i + p);
+        reinterpret_cast<f4*>(a.out)[(j * C::N + k) * a.M + m] = q;
       }
     }
   }
   if (INTEGRATE) {
     if (lane_ok && hi > lo) {
 #pragma unroll
-      for (int e = 0; e < C::E; ++e) {
-        float* o = a.out + (((b * C::N) + (t + C::T * e)) * a.M + m) * 4;
-        atomic_add(o + 0, acc[e].x);
-        atomic_add(o + 1, acc[e].y);
-        atomic_add(o + 2, acc[e].z);
-        atomic_add(o + 3, acc[e].w);
+      for (int i = 0; i < C::E / 2; ++i) {
+        const int k = t + C::T * (2 * i + p);
+        float* o = a.out + ((b * C::N + k) * a.M + m) * 4;
+        atomic_add(o + 0, acc[i].x);
+        atomic_add(o + 1, acc[i].y);
+        atomic_add(o + 2, acc[i].z);
+        atomic_add(o + 3, acc[i].w);
       }
     }
     if (tid == 0 && blockIdx.x == 0 && hi > lo)

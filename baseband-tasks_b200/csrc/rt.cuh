@@ -60,6 +60,18 @@ inline unsigned long long atomic_add(unsigned long long* p,
                                      unsigned long long v) {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+}  // namespace bbt
+float* bbt_emu_scratch();
+namespace bbt {
+// Exchange with the neighbouring thread (lane ^ 1), as __shfl_xor_sync does.
+inline float shfl_xor1(float v) {
+  float* s = bbt_emu_scratch();
+  s[threadIdx.x] = v;
+  bbt_emu_syncthreads();
+  const float r = s[threadIdx.x ^ 1];
+  bbt_emu_syncthreads();
+  return r;
+}
 inline void sincospi_d(double x, double* s, double* c) {
   *s = sin(M_PI * x);
   *c = cos(M_PI * x);
@@ -128,6 +140,9 @@ __device__ __forceinline__ unsigned long long atomic_add(
 }
 __device__ __forceinline__ void sincospi_d(double x, double* s, double* c) {
   sincospi(x, s, c);
+}
+__device__ __forceinline__ float shfl_xor1(float v) {
+  return __shfl_xor_sync(0xffffffffu, v, 1);
 }
 // Explicitly rounded double arithmetic (no FMA contraction): the fold-bin
 // assignment must match the oracle's numpy float64 operations bit for bit.

@@ -149,6 +149,8 @@ int bbt_average_exec(const void* sum, const void* count, void* out,
  * bbt_profile_report: wait for them and write "kernel count total_ms" lines
  * (NUL-terminated) into buf, clearing the records. */
 int64_t bbt_launch_count(void);
+/* Development knob: select among compiled tile shapes (key 1: channelizer). */
+int bbt_tune(int key, int value);
 int bbt_profile_enable(int on);
 int bbt_profile_report(char* buf, int64_t size);
 

@@ -14,8 +14,10 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static thread_local std::barrier<>* t_barrier = nullptr;
 static thread_local void* t_smem = nullptr;
+static thread_local float* t_scratch = nullptr;
 
 void* bbt_emu_smem() { return t_smem; }
+float* bbt_emu_scratch() { return t_scratch; }
 void bbt_emu_syncthreads() {
   if (t_barrier) t_barrier->arrive_and_wait();
 }
@@ -25,12 +27,14 @@ void bbt_emu_launch(dim3 grid, dim3 block, size_t smem,
   const unsigned nthreads = block.x * block.y * block.z;
   std::barrier<> bar(nthreads);
   std::vector<char> shared(smem + 64);
+  std::vector<float> scratch(nthreads + 1);
   std::vector<std::thread> pool;
   pool.reserve(nthreads);
   for (unsigned tid = 0; tid < nthreads; ++tid) {
     pool.emplace_back([&, tid]() {
       t_barrier = &bar;
       t_smem = shared.data();
+      t_scratch = scratch.data();
       blockDim = block;
       gridDim = grid;
       threadIdx = dim3(tid % block.x, (tid / block.x) % block.y,

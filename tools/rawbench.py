@@ -151,6 +151,14 @@ def sec_dd():
 
 
 def sec_chan():
+    for variant in (0, 1, 2, 3, 4):
+        lib.bbt_tune(1, variant)
+        print('channelizer tile variant', variant)
+        _sec_chan()
+    lib.bbt_tune(1, 0)
+
+
+def _sec_chan():
     n, m = 1024, 8
     n_spec = 1 << 13
     x = torch.randn(n_spec * n * m * 2, dtype=torch.complex64, device=dev)
