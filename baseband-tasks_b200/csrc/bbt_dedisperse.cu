@@ -10,6 +10,7 @@ struct bbt_dedisperse_plan {
   int planar;      // work-buffer layout of the three-pass split
   int col_e32;     // 32 elements per thread in short column FFTs
   int row16;       // 16 elements per thread in the row FFTs
+  int half;        // 256-thread CTAs, half-size tiles
   const cf* tw;
   cf* big_lo;
   cf* big_hi;
@@ -21,11 +22,12 @@ namespace {
 
 constexpr int kColThreads = 512;
 
-// Elements per thread of the column FFTs.
-template <int L1, bool E32>
+// Elements per thread of the column FFTs.  HALF: 256-thread CTAs with half
+// the lanes (64 KB tiles, two CTAs per SM).
+template <int L1, bool E32, bool HALF>
 struct ColCfg {
   static constexpr int LOG2E = L1 <= 4 ? L1 : ((L1 <= 8 && !E32) ? 4 : 5);
-  using type = FftCfg<L1, LOG2E, kColThreads>;
+  using type = FftCfg<L1, LOG2E, HALF ? kColThreads / 2 : kColThreads>;
 };
 
 int col_lanes(int l1, bool e32) {
@@ -33,10 +35,12 @@ int col_lanes(int l1, bool e32) {
   return kColThreads >> (l1 - log2e);
 }
 
-template <int L1, bool E32>
-int launch_dd_col(bool inverse, const DdArgs& a, int64_t n_frames,
+template <int L1, bool E32, bool HALF = false>
+int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
                   bbt_stream_t st) {
-  using C = typename ColCfg<L1, E32>::type;
+  using C = typename ColCfg<L1, E32, HALF>::type;
+  DdArgs a = a0;
+  if (HALF) a.ahead *= 2;
   const int64_t cols = (a.N >> L1) * a.S;
   dim3 grid((unsigned)ceil_div(cols, C::G), (unsigned)n_frames);
   const size_t smem = C::SMEM_BYTES;
@@ -50,10 +54,12 @@ int launch_dd_col(bool inverse, const DdArgs& a, int64_t n_frames,
 
 // ROW16: 16 elements per thread in 1024-thread CTAs instead of 32 in 512 (or
 // 256 for planar rows below 2^14 points, two CTAs per SM).
-template <int L2, bool PLANAR, bool ROW16>
-int launch_dd_row(const DdArgs& a, int64_t n_frames, bbt_stream_t st) {
+template <int L2, bool PLANAR, bool ROW16, bool HALF = false>
+int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   using C = FftCfg<L2, ROW16 ? 4 : 5,
-                   ROW16 ? 1024 : 512>;
+                   ROW16 ? 1024 : (HALF ? 256 : 512)>;
+  DdArgs a = a0;
+  if (HALF) a.ahead *= 2;
   const int64_t n1 = a.N >> L2;
   int64_t blocks;
   if (PLANAR) {
@@ -135,6 +141,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->planar = 1;
   p->col_e32 = (hint >> 10) & 1;
   p->row16 = (hint >> 11) & 1;
+  p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
   const int hint_l1 = hint & 0xff;
   const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;
   if (l <= kLog2TwiddleTable && (n_series == 1 || l <= 10) && !hint_l1) {
@@ -167,6 +174,9 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     p->log2n1 = l1;
     p->log2n2 = l2;
     p->planar = planar ? 1 : 0;
+    // Interleaved rows run as two 64 KB tiles per SM (measured: a little
+    // faster than one 128 KB tile); bit 14 of the hint switches that off.
+    if (!planar && !((hint >> 14) & 1)) p->half |= 2;
   }
   p->tw = twiddle_table();
   void* d = nullptr;
@@ -326,26 +336,34 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
   }
   if (!work) return fail(BBT_EINVAL, "dedispersion needs a work buffer");
   const bool e32 = p->col_e32;
-#define F(L)                                                         \
-  rc = e32 ? launch_dd_col<L, true>(false, a, n_frames, st)          \
-           : launch_dd_col<L, false>(false, a, n_frames, st)
+  const bool hcol = p->half & 1, hrow = p->half & 2;
+#define F(L)                                                              \
+  rc = hcol ? launch_dd_col<L, false, true>(false, a, n_frames, st)       \
+            : (e32 ? launch_dd_col<L, true>(false, a, n_frames, st)       \
+                   : launch_dd_col<L, false>(false, a, n_frames, st))
   BBT_FOR_LOG2(p->log2n1, F)
 #undef F
   if (rc) return rc;
   rc = BBT_EUNSUPPORTED;
-#define F(L)                                                           \
-  rc = p->planar ? (p->row16 ? launch_dd_row<L, true, true>(a, n_frames, st)   \
-                             : launch_dd_row<L, true, false>(a, n_frames, st)) \
-                 : (p->row16                                                   \
-                        ? launch_dd_row<L, false, true>(a, n_frames, st)       \
-                        : launch_dd_row<L, false, false>(a, n_frames, st))
+#define F(L)                                                                  \
+  rc = hrow ? (p->planar                                                      \
+                   ? launch_dd_row<L, true, false, true>(a, n_frames, st)     \
+                   : launch_dd_row<L, false, false, true>(a, n_frames, st))   \
+            : (p->planar                                                      \
+                   ? (p->row16                                                \
+                          ? launch_dd_row<L, true, true>(a, n_frames, st)     \
+                          : launch_dd_row<L, true, false>(a, n_frames, st))   \
+                   : (p->row16                                                \
+                          ? launch_dd_row<L, false, true>(a, n_frames, st)    \
+                          : launch_dd_row<L, false, false>(a, n_frames, st)))
   BBT_FOR_ROW(p->log2n2, F)
 #undef F
   if (rc) return rc;
   rc = BBT_EUNSUPPORTED;
-#define F(L)                                                         \
-  rc = e32 ? launch_dd_col<L, true>(true, a, n_frames, st)           \
-           : launch_dd_col<L, false>(true, a, n_frames, st)
+#define F(L)                                                              \
+  rc = hcol ? launch_dd_col<L, false, true>(true, a, n_frames, st)        \
+            : (e32 ? launch_dd_col<L, true>(true, a, n_frames, st)        \
+                   : launch_dd_col<L, false>(true, a, n_frames, st))
   BBT_FOR_LOG2(p->log2n1, F)
 #undef F
   return rc;

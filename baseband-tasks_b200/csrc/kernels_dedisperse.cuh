@@ -59,7 +59,8 @@ BBT_HD void prefetch_tile(const cf* base, long long rows, long long stride,
 // Pass 1: forward column FFTs, frame -> work.  Lanes are consecutive flat
 // columns q = n2*S + s.
 template <class C>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    dd_col_fwd_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long n2s = (a.N >> a.log2n1) * a.S;  // N2*S columns
   const int tid = threadIdx.x;
@@ -118,7 +119,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_fwd_kernel(DdArgs a) {
 
 // Pass 3: inverse column FFTs, work -> valid part of the output stream.
 template <class C>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_col_inv_kernel(DdArgs a) {
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    dd_col_inv_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long n2s = (a.N >> a.log2n1) * a.S;
   const int tid = threadIdx.x;
@@ -207,7 +209,8 @@ BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
 // rows when S < G) of the interleaved buffer, consecutive threads taking
 // consecutive series.
 template <class C, bool PLANAR>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_kernel(DdArgs a) {
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    dd_row_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   const long long n1 = a.N >> a.log2n2;
   const int tid = threadIdx.x;

@@ -246,6 +246,7 @@ INTER, E32, R16 = 512, 1024, 2048   # plan hints: layout, thread shapes
     (14, 1, 0), (14, 2, 0), (15, 3, 5), (16, 2, 3), (14, 2, 4 | INTER),
     (13, 16, INTER), (15, 3, 5 | INTER | E32), (15, 1, 5 | E32),
     (15, 1, 5 | R16), (14, 2, 4 | INTER | R16), (24, 2, R16),
+    (15, 2, 5 | 4096 | 8192), (14, 16, 4 | INTER | 4096 | 8192),
     (20, 2, 0), (20, 16, 0), (20, 16, INTER), (20, 16, 6 | E32),
     (22, 2, 10), (24, 2, 0)])
 def test_dedisperse_large(backend, log2n, S, log2n1):

@@ -122,10 +122,11 @@ def dd_plan(N, S, pad_start, n_valid, log2n1):
 def sec_dd():
     # planar, interleaved, E=32 column FFTs, 16-element row FFTs
     P, I, E, R = 256, 512, 1024, 2048
+    HC, HR = 4096, 8192   # half-size tiles in column / row passes
     for (N, S, frames, hints) in (
-            (1 << 20, 16, 4, (I, I | R, 0, R, 7 | P, 7 | P | R, 9 | I)),
-            (1 << 24, 2, 2, (0, R, 11 | P, 11 | P | R)),
-            (1 << 22, 2, 4, (0, R, 9 | P, 9 | P | R)),
+            (1 << 20, 16, 4, (I, I | HC, I | HR, I | HC | HR)),
+            (1 << 24, 2, 2, (0, HC, 11 | P | HR)),
+            (1 << 22, 2, 4, (0, HC, 9 | P | HR, 9 | P | HC | HR)),
             (1 << 14, 2050, 2, (0,)),
             (1 << 13, 2050, 4, (0,))):
         pad = N // 5
