@@ -246,6 +246,35 @@ class Integrate(BaseTaskBase):
     def _frame_dependent(self):
         return False
 
+    def read_sums(self, count=None):
+        """Sums and counts of the next ``count`` output samples, on the device.
+
+        Returns ``(sums, counts)``: float32 sums with the shape of the output
+        samples (complex streams as real, imaginary pairs in the last axis)
+        and int64 counts per bin.  This is what is reduced over ranks when a
+        stream is sharded in time (`baseband_tasks_b200.parallel`).
+        """
+        count = self._check_read(count, None)
+        a = self.offset
+        saved, self._raw_sums = getattr(self, '_raw_sums', False), True
+        try:
+            if self._frame_dependent():
+                parts = []
+                spf = self.samples_per_frame
+                pos = a
+                while pos < a + count:
+                    n = min(a + count - pos, spf - pos % spf)
+                    parts.append(self._integrate_samples(pos, n))
+                    pos += n
+                sums = B.torch().cat([p[0] for p in parts])
+                cnts = B.torch().cat([p[1] for p in parts])
+            else:
+                sums, cnts = self._integrate_samples(a, count)
+        finally:
+            self._raw_sums = saved
+        self.offset = a + count
+        return sums, cnts
+
     def _integrate_samples(self, sample0, n_sample):
         """Output samples [sample0, sample0 + n_sample)."""
         samples = np.arange(sample0, sample0 + n_sample + 1)
@@ -260,6 +289,8 @@ class Integrate(BaseTaskBase):
 
     def _finish(self, sums, count, shape):
         """Average on the device, or assemble the structured host array."""
+        if getattr(self, '_raw_sums', False):
+            return sums, count
         lib = _cabi.lib()
         ih_dtype = np.dtype(self.ih.dtype)
         single = np.complex64 if ih_dtype.kind == 'c' else np.float32

@@ -32,8 +32,12 @@ def build_emu():
                if f.endswith(('.cu', '.cuh'))]
     sources += [os.path.join(EMU_DIR, 'bbt_emu.cpp'),
                 os.path.join(ROOT, 'include', 'bbt_b200.h')]
-    if _stale(EMU_LIB, sources):
-        subprocess.run(['sh', os.path.join(EMU_DIR, 'build.sh')], check=True)
+    import fcntl
+    with open(os.path.join(EMU_DIR, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)     # one builder at a time
+        if _stale(EMU_LIB, sources):
+            subprocess.run(['sh', os.path.join(EMU_DIR, 'build.sh')],
+                           check=True)
     return EMU_LIB
 
 
