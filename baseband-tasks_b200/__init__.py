@@ -16,6 +16,8 @@ from .fourier import fft_maker, CudaFFTMaker  # noqa: F401
 from .dm import DispersionMeasure  # noqa: F401
 from .dispersion import Disperse, Dedisperse  # noqa: F401
 from .channelize import Channelize, Dechannelize  # noqa: F401
+from .pfb import (sinc_hamming, PolyphaseFilterBankSamples,  # noqa: F401
+                  PolyphaseFilterBank)
 from .functions import Square, Power  # noqa: F401
 from .integration import Integrate, Fold, PolynomialPhase  # noqa: F401
 from .generators import (StreamGenerator, EmptyStreamGenerator, Noise,  # noqa

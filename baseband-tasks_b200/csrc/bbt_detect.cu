@@ -206,6 +206,7 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
       1, std::min<int64_t>(ceil_div((int64_t)sm_count() * 8, n_bins),
                            ceil_div(n, n_bins * 1024)));
   dim3 grid((unsigned)chunks, (unsigned)n_bins);
+  prof_next_name = "fold";
   if (power)
     BBT_LAUNCH(fold_kernel<true>, grid, dim3(256), a.use_smem ? smem : 0,
                as_stream(stream), a);
@@ -213,6 +214,50 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
     BBT_LAUNCH(fold_kernel<false>, grid, dim3(256), a.use_smem ? smem : 0,
                as_stream(stream), a);
   return check_launch("fold kernel");
+}
+
+}  // extern "C"
+namespace {
+template <int L>
+int launch_pfb(const PfbArgs& a, bool real, bbt_stream_t st) {
+  using D = DefaultCfg<L>;
+  using C = FftCfg<L, D::LOG2E, 256>;
+  const int64_t blocks = ceil_div(a.n_spec * a.inner, C::G);
+  if (blocks > 2147483647LL) return fail(BBT_EUNSUPPORTED, "grid too large");
+  const size_t smem = C::SMEM_BYTES;
+  auto kern = real ? pfb_kernel<C, true> : pfb_kernel<C, false>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "pfb";
+  BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a);
+  return check_launch("polyphase filter bank kernel");
+}
+}  // namespace
+extern "C" {
+
+int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
+                 int64_t n_tap, int64_t inner, int64_t n_spec, int is_real,
+                 void* stream) {
+  if (!in || !out || !response) return fail(BBT_EINVAL, "null argument");
+  if (!is_pow2(n) || n < 2 || n > 8192)
+    return fail(BBT_EUNSUPPORTED,
+                "polyphase filter bank needs a power-of-two number of "
+                "samples per spectrum in [2, 8192]");
+  if (n_tap < 1 || inner < 1) return fail(BBT_EINVAL, "bad filter bank shape");
+  if (n_spec <= 0) return BBT_OK;
+  PfbArgs a;
+  a.in = in;
+  a.out = static_cast<cf*>(out);
+  a.h = static_cast<const float*>(response);
+  a.tw = twiddle_table();
+  a.inner = inner;
+  a.n_spec = n_spec;
+  a.n_tap = (int)n_tap;
+  int rc = BBT_EUNSUPPORTED;
+#define F(L) rc = launch_pfb<L>(a, is_real != 0, as_stream(stream))
+  BBT_FOR_LOG2(ilog2(n), F)
+#undef F
+  return rc;
 }
 
 int bbt_average_exec(const void* sum, const void* count, void* out,

@@ -280,6 +280,11 @@ BBT_HD cf ld_stream(const cf* p) {
   return *p;
 #endif
 }
+#if defined(__CUDA_ARCH__)
+#define BBT_LDGF(p) __ldg(p)
+#else
+#define BBT_LDGF(p) (*(p))
+#endif
 BBT_HD void prefetch_l2(const void* p) {
 #if defined(__CUDA_ARCH__)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

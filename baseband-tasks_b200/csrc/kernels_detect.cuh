@@ -293,6 +293,63 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Polyphase filter bank, FIR and FFT fused (pfb.py:91-100 then
+// channelize.py:73-74): spectrum j of column c is
+//   FFT_n( sum_{tap < n_tap} h[tap][i] * x[((j + tap) n + i)][c] )_i .
+// Lanes are (spectrum, column) pairs with the column fastest; REAL input keeps
+// the n/2+1 non-negative frequencies (fourier/numpy.py:41-43).
+struct PfbArgs {
+  const void* in;     // [(n_spec + n_tap - 1) * n][inner] float or complex
+  cf* out;            // [n_spec][n_chan][inner]
+  const float* h;     // [n_tap][n]
+  const cf* tw;
+  long long inner, n_spec;
+  int n_tap;
+};
+
+template <class C, bool REAL>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
+  cf* smem = BBT_SMEM(cf);
+  const int tid = threadIdx.x;
+  const int g = tid % C::G, t = tid / C::G;
+  const long long lane = (long long)blockIdx.x * C::G + g;
+  const long long j = lane / a.inner, c = lane % a.inner;
+  const bool valid = j < a.n_spec;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) v[e] = mk(0.f, 0.f);
+  if (valid) {
+    for (int tap = 0; tap < a.n_tap; ++tap) {
+      const float* h = a.h + (long long)tap * C::N;
+      const long long base = ((j + tap) * C::N) * a.inner + c;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        const int i = t + C::T * e;
+        const float w = BBT_LDGF(h + i);
+        if (REAL) {
+          v[e].x += w * static_cast<const float*>(a.in)[base + i * a.inner];
+        } else {
+          const cf x = static_cast<const cf*>(a.in)[base + i * a.inner];
+          v[e].x += w * x.x;
+          v[e].y += w * x.y;
+        }
+      }
+    }
+  }
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  block_fft<C>(v, t, a.tw, sm);
+  if (valid) {
+    const long long n_chan = REAL ? C::N / 2 + 1 : C::N;
+    cf* dst = a.out + (j * n_chan) * a.inner + c;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      const int k = t + C::T * e;
+      if (!REAL || k <= C::N / 2) dst[k * a.inner] = v[e];
+    }
+  }
+}
+
 // out[b][c] = sum[b][c] / count[b]; 0/0 gives NaN like numpy's division.
 BBT_GLOBAL void average_kernel(const float* BBT_RESTRICT sum,
                                const unsigned long long* BBT_RESTRICT count,

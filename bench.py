@@ -49,6 +49,14 @@ WORKLOADS = {
                log2n=24, frames=4, n_chan=1024, step=1e-3, seed=1234567 + 4,
                desc='2pol x 512 MHz c64 -> Dedisperse(DM=1000, N=2^24) -> '
                     'Channelize(1024) -> Power -> Integrate(1 ms)'),
+    # configs[4]: fold with a polynomial phase; profiles reduced over ranks.
+    'C5': dict(rate=512e6, freq=8192e6, sample_shape=(2,), dm=1000.,
+               log2n=24, frames=4, n_chan=None, step=None, seed=1234567 + 5,
+               fold=dict(n_phase=512, coef=[0.25, 29.946923,
+                                            -3.77535e-10 / 2.]),
+               desc='2pol x 512 MHz c64 -> Dedisperse(DM=1000, N=2^24) -> '
+                    'Power -> Fold(512 bins, polynomial phase), NCCL reduce '
+                    'of the profile'),
 }
 
 
@@ -77,6 +85,8 @@ def model_bytes(w):
     """Pre-registered algorithmic bytes per source sample."""
     N, spf, _, _ = framing(w)
     eff = spf / N
+    if w.get('fold'):
+        return 48. / eff + 8.
     per_bin = w['step'] * w['rate'] / w['n_chan']
     return 48. / eff + 8. + 8. / per_bin
 
@@ -154,6 +164,12 @@ def build_chain(w, data, start):
                          frequency=w['freq'], sideband=1, polarization=pol)
     dd = bt.Dedisperse(src, w['dm'], samples_per_frame=spf)
     assert dd._ih_samples_per_frame == N, (dd._ih_samples_per_frame, N)
+    if w.get('fold'):
+        # Phase polynomial referred to the start of the whole stream, so all
+        # ranks fold on the same ephemeris.
+        poly = bt.PolynomialPhase(w['fold']['coef'], bt.Time(1289567655))
+        return src, bt.Fold(bt.Power(dd), w['fold']['n_phase'], poly,
+                            average=False)
     ch = bt.Channelize(dd, w['n_chan'])
     pw = bt.Power(ch)
     it = bt.Integrate(pw, w['step'])
@@ -187,9 +203,20 @@ def run_b200(args):
     src, chain = build_chain(w, dev_in, start)
     out_host = None
 
+    from baseband_tasks_b200 import parallel
+    folding = bool(w.get('fold'))
+
+    def run_chain(c):
+        c.seek(0)
+        if not folding:
+            return c.read_device()
+        # Profile sums and counts, summed over ranks (NCCL over NVLink).
+        sums, counts = c.read_sums()
+        parallel.reduce_sums(sums, counts)
+        return sums
+
     def step_resident():
-        chain.seek(0)
-        return chain.read_device()
+        return run_chain(chain)
 
     # End to end: pinned host block -> device -> chain -> host.
     dev_stage = torch.empty_like(dev_in)
@@ -198,8 +225,7 @@ def run_b200(args):
     def step_e2e():
         nonlocal out_host
         dev_stage.copy_(host, non_blocking=True)
-        chain_e2e.seek(0)
-        res = chain_e2e.read_device()
+        res = run_chain(chain_e2e)
         if out_host is None:
             out_host = torch.empty(res.shape, dtype=res.dtype,
                                    pin_memory=True)
@@ -272,7 +298,8 @@ def run_b200(args):
     points = w['frames'] * N * S              # FFT points per dedisperse pass
     alg = {'dd_col_fwd': 16. * points, 'dd_row': 16. * points,
            'dd_col_inv': 8. * points + 8. * w['frames'] * spf * S,
-           'chanpow_integrate': 8. * samples_per_step + out_bytes}
+           'chanpow_integrate': 8. * samples_per_step + out_bytes,
+           'fold': 8. * samples_per_step}
     top = max((k for k in kernels if k in alg),
               key=lambda k: kernels[k][1], default=None)
     roofline = None
@@ -301,8 +328,9 @@ def run_b200(args):
     mb = model_bytes(w)
     cpu = cpu_baseline(w, budget_s=15.)
     line = {
-        'metric': 'Dedisperse->Channelize->Power->Integrate complex '
-                  'Gsamples/s',
+        'metric': ('Dedisperse->Power->Fold complex Gsamples/s' if folding
+                   else 'Dedisperse->Channelize->Power->Integrate complex '
+                   'Gsamples/s'),
         'value': value, 'unit': 'Gsamples/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -315,7 +343,9 @@ def run_b200(args):
                    'l2': 'inputs (%.2f GB per step) larger than L2'
                          % (host_np.nbytes / 1e9),
                    'sharding': 'time blocks with overlap-save halo, one per '
-                               'rank; no collective'},
+                               'rank; ' + ('NCCL all-reduce of the folded '
+                                           'profile' if folding
+                                           else 'no collective')},
         'e2e': {'value': e2e, 'unit': 'Gsamples/s',
                 'h2d_bytes_per_step': int(host_np.nbytes),
                 'd2h_bytes_per_step': int(out_bytes),
@@ -360,12 +390,25 @@ def _cpu_unit(args):
     pf = plan.phase_factor('c8')
     t1 = time.perf_counter()
     y = orc.disperse(x, plan, phase_factor=pf)
-    spectra = orc.channelize(y, w['n_chan'])
-    power = orc.power(spectra, axis=-1)
-    ip = orc.IntegratePlan(power.shape[0], w['rate'] / w['n_chan'],
-                           w['step'])
-    offsets = ip.offsets(np.arange(ip.n_out + 1))
-    orc.integrate(power, offsets)
+    if w.get('fold'):
+        power = orc.power(y, axis=-1)
+        coef = w['fold']['coef']
+
+        def phase(i):
+            dt = i.astype(np.float64) / w['rate']
+            ph = np.full(dt.shape, coef[-1])
+            for c in coef[-2::-1]:
+                ph = ph * dt + c
+            return ph
+        orc.fold(power, np.array([0, power.shape[0]]), w['fold']['n_phase'],
+                 phase)
+    else:
+        spectra = orc.channelize(y, w['n_chan'])
+        power = orc.power(spectra, axis=-1)
+        ip = orc.IntegratePlan(power.shape[0], w['rate'] / w['n_chan'],
+                               w['step'])
+        offsets = ip.offsets(np.arange(ip.n_out + 1))
+        orc.integrate(power, offsets)
     t2 = time.perf_counter()
     return spf * npol, t2 - t1, t1 - t0
 

@@ -526,3 +526,58 @@ def test_noise_generator_reproducible(bt):
     nh.seek(0)
     full = nh.read()
     assert abs(full.real.std() - 1.) < 0.02 and abs(full.mean()) < 0.02
+
+
+# ---------------------------------------------------------------------- pfb
+def test_sinc_hamming_guppi(bt):
+    """tests/test_pfb.py:26-35: the GUPPI coefficients."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), 'golden',
+                        'guppi_pfb_coeffs.txt')
+    coeffs = np.loadtxt(path).reshape(8, -1).T.reshape(12, 64)
+    from baseband_tasks_b200.pfb import sinc_hamming
+    np.testing.assert_allclose(sinc_hamming(12, 64, sinc_scale=0.95), coeffs)
+
+
+@pytest.mark.parametrize('dtype,shape', [('f4', ()), ('f4', (2,)),
+                                         ('c8', (3,))])
+def test_polyphase_filter_bank(bt, dtype, shape):
+    """tests/test_pfb.py:54-102 (single precision): the filter bank equals
+    rfft((h * d[i:i+4]).sum(0)), at the start and at an offset."""
+    from baseband_tasks_b200.pfb import sinc_hamming
+    n, n_tap = 64, 4
+    n_in = 40 * n
+    rng = np.random.default_rng(12345)
+    x = rng.normal(size=(n_in,) + shape)
+    if dtype == 'c8':
+        x = x + 1j * rng.normal(size=(n_in,) + shape)
+    x = x.astype(dtype)
+    response = sinc_hamming(n_tap, n)
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=128,
+                         frequency=300e6, sideband=1)
+    for cls in (bt.PolyphaseFilterBankSamples, bt.PolyphaseFilterBank):
+        pfb = cls(src, response)
+        want = orc.pfb(x.astype('f8' if dtype == 'f4' else 'c16'), response,
+                       ih_samples_per_frame=128)
+        n_chan = n // 2 + 1 if dtype == 'f4' else n
+        assert pfb.shape == want.shape == (want.shape[0], n_chan) + shape
+        assert pfb.dtype == np.complex64
+        assert pfb.sample_rate == 1e6 / n
+        assert abs((pfb.start_time - src.start_time)
+                   - (n_tap - 1) * n / 2 / 1e6) < 1e-12
+        got = pfb.read()
+        assert_voltage(got, want.astype('c8'))
+        # Direct definition at an offset.
+        h = response.reshape(response.shape + (1,) * len(shape))
+        j = 17
+        d = x[j * n:(j + n_tap) * n].reshape((n_tap, n) + shape)
+        direct = (np.fft.rfft if dtype == 'f4' else np.fft.fft)(
+            (h * d).sum(0), axis=0)
+        pfb.seek(j)
+        assert_voltage(pfb.read(1)[0], direct.astype('c8'))
+        np.testing.assert_array_equal(
+            pfb.frequency, orc.channelize_frequency(
+                300e6, 1, n, 1e6, dtype == 'f4', len(shape)))
+    pfb2 = bt.PolyphaseFilterBank(src, response, samples_per_frame=5)
+    assert pfb2.samples_per_frame == 5
+    assert_voltage(pfb2.read(), want[:pfb2.shape[0]].astype('c8'))
