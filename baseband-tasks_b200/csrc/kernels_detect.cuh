@@ -230,10 +230,18 @@ BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
   const double dt = ddiv(dadd((double)i_abs, -a.i_ref), a.rate);
   double ph = a.coef[a.ncoef - 1];
   for (int k = a.ncoef - 2; k >= 0; --k) ph = dadd(dmul(ph, dt), a.coef[k]);
-  double r = fmod(ph, 1.0);
+  // fmod(ph, 1) is exactly ph - trunc(ph) (the difference is representable).
+  double r = dadd(ph, -trunc(ph));
   if (r < 0.) r = dadd(r, 1.0);  // numpy's floored modulo
   return (int)dmul(r, (double)a.n_phase);
 }
+
+// Consecutive samples mostly fall in the same phase bin (a bin lasts many
+// samples), so a warp first checks whether all its 32 samples share one bin;
+// if so it reduces them with shuffles and lane 0 adds the total to a running
+// per-warp accumulator that is only flushed (one atomic per value) when the
+// bin changes.  Mixed warps fall back to one shared-memory atomic per sample.
+constexpr int kFoldFast = 8;  // most values per sample kept in registers
 
 template <bool POWER>
 BBT_GLOBAL void fold_kernel(FoldArgs a) {
@@ -256,32 +264,116 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
   float* gsum = a.sum + b * (long long)nh;
   unsigned long long* gcnt = a.count + b * a.n_phase;
   const long long width = POWER ? a.inner / 4 : a.inner;  // input items per sample
-  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    int p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
-    if (p < 0) p = 0;
-    if (p >= a.n_phase) p = a.n_phase - 1;
-    float* dsum = (a.use_smem ? hist : gsum) + (long long)p * a.inner;
-    if (POWER) {
-      const cf2* x = static_cast<const cf2*>(a.in) + i * width;
-      for (long long m = 0; m < width; ++m) {
-        const f4 q = stokes_like(x[m].a, x[m].b);
-        atomic_add(dsum + 4 * m + 0, q.x);
-        atomic_add(dsum + 4 * m + 1, q.y);
-        atomic_add(dsum + 4 * m + 2, q.z);
-        atomic_add(dsum + 4 * m + 3, q.w);
+#if defined(__CUDA_ARCH__)
+  if (a.use_smem && a.inner <= kFoldFast) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float acc[kFoldFast];
+#pragma unroll
+    for (int c = 0; c < kFoldFast; ++c) acc[c] = 0.f;
+    unsigned acc_n = 0;
+    int cur = -1;
+    const int inner = (int)a.inner;
+    // All threads of a warp run the same number of iterations.
+    for (long long ib = i0 + (threadIdx.x - lane); ib < i1; ib += blockDim.x) {
+      const long long i = ib + lane;
+      const bool ok = i < i1;
+      int p = -1;
+      float x[kFoldFast];
+#pragma unroll
+      for (int c = 0; c < kFoldFast; ++c) x[c] = 0.f;
+      if (ok) {
+        p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
+        if (p < 0) p = 0;
+        if (p >= a.n_phase) p = a.n_phase - 1;
+        if (POWER) {
+          const cf2* src = static_cast<const cf2*>(a.in) + i * width;
+#pragma unroll
+          for (int m = 0; m < kFoldFast / 4; ++m) {
+            if (m < width) {
+              const f4 q = stokes_like(src[m].a, src[m].b);
+              x[4 * m] = q.x;
+              x[4 * m + 1] = q.y;
+              x[4 * m + 2] = q.z;
+              x[4 * m + 3] = q.w;
+            }
+          }
+        } else {
+          const float* src = static_cast<const float*>(a.in) + i * width;
+#pragma unroll
+          for (int c = 0; c < kFoldFast; ++c)
+            if (c < inner) x[c] = src[c];
+        }
       }
-    } else {
-      const float* x = static_cast<const float*>(a.in) + i * width;
-      for (long long c = 0; c < width; ++c) atomic_add(dsum + c, x[c]);
+      const int p0 = __shfl_sync(full, p, 0);
+      if (__all_sync(full, p == p0)) {
+        // One bin for the whole warp (p0 >= 0 since lane 0 is in range).
+#pragma unroll
+        for (int c = 0; c < kFoldFast; ++c) {
+          if (c < inner) {
+            float r = x[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(full, r, o);
+            x[c] = r;
+          }
+        }
+        if (lane == 0) {
+          if (p0 != cur) {
+            if (cur >= 0) {
+              for (int c = 0; c < inner; ++c)
+                atomicAdd(hist + cur * inner + c, acc[c]);
+              atomicAdd(hcnt + cur, acc_n);
+            }
+            cur = p0;
+            acc_n = 0;
+#pragma unroll
+            for (int c = 0; c < kFoldFast; ++c) acc[c] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < kFoldFast; ++c) acc[c] += x[c];
+          acc_n += 32;
+        }
+      } else if (ok) {
+#pragma unroll
+        for (int c = 0; c < kFoldFast; ++c)
+          if (c < inner) atomicAdd(hist + p * inner + c, x[c]);
+        atomicAdd(hcnt + p, 1u);
+      }
     }
-    if (a.use_smem) {
-#if defined(BBT_EMULATE)
-      __atomic_fetch_add(hcnt + p, 1u, __ATOMIC_RELAXED);
-#else
-      atomicAdd(hcnt + p, 1u);
+    if (lane == 0 && cur >= 0) {
+      for (int c = 0; c < inner; ++c) atomicAdd(hist + cur * inner + c, acc[c]);
+      atomicAdd(hcnt + cur, acc_n);
+    }
+  } else
 #endif
-    } else {
-      atomic_add(gcnt + p, 1ull);
+  {
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      int p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
+      if (p < 0) p = 0;
+      if (p >= a.n_phase) p = a.n_phase - 1;
+      float* dsum = (a.use_smem ? hist : gsum) + (long long)p * a.inner;
+      if (POWER) {
+        const cf2* x = static_cast<const cf2*>(a.in) + i * width;
+        for (long long m = 0; m < width; ++m) {
+          const f4 q = stokes_like(x[m].a, x[m].b);
+          atomic_add(dsum + 4 * m + 0, q.x);
+          atomic_add(dsum + 4 * m + 1, q.y);
+          atomic_add(dsum + 4 * m + 2, q.z);
+          atomic_add(dsum + 4 * m + 3, q.w);
+        }
+      } else {
+        const float* x = static_cast<const float*>(a.in) + i * width;
+        for (long long c = 0; c < width; ++c) atomic_add(dsum + c, x[c]);
+      }
+      if (a.use_smem) {
+#if defined(BBT_EMULATE)
+        __atomic_fetch_add(hcnt + p, 1u, __ATOMIC_RELAXED);
+#else
+        atomicAdd(hcnt + p, 1u);
+#endif
+      } else {
+        atomic_add(gcnt + p, 1ull);
+      }
     }
   }
   if (a.use_smem) {
