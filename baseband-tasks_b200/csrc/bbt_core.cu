@@ -92,15 +92,16 @@ cf* make_roots(int64_t count, double denom) {
   return static_cast<cf*>(dev);
 }
 
-const cf* twiddle_table() {
+const cf* twiddle_table(int log2n) {
   static std::mutex mu;
-  static std::map<int, cf*> tables;
+  static std::map<std::pair<int, int>, cf*> tables;
   std::lock_guard<std::mutex> lock(mu);
-  const int dev = current_device();
-  auto it = tables.find(dev);
+  const std::pair<int, int> key(current_device(), log2n);
+  auto it = tables.find(key);
   if (it != tables.end()) return it->second;
-  cf* t = make_roots(kTwiddleTable, (double)kTwiddleTable);
-  tables[dev] = t;
+  const int64_t n = int64_t(1) << log2n;
+  cf* t = make_roots(n, (double)n);
+  tables[key] = t;
   return t;
 }
 

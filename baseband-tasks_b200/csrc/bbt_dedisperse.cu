@@ -11,7 +11,8 @@ struct bbt_dedisperse_plan {
   int col_e32;     // 32 elements per thread in short column FFTs
   int row16;       // 16 elements per thread in the row FFTs
   int half;        // 256-thread CTAs, half-size tiles
-  const cf* tw;
+  const cf* tw1;   // roots of unity for the column FFTs (n1)
+  const cf* tw2;   // for the row FFTs (n2), or the whole single-pass frame
   cf* big_lo;
   cf* big_hi;
   cf* chirp;        // [n_chirp][n1][n2]
@@ -69,7 +70,9 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
     const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
     blocks = ceil_div(n1, rpc) * ceil_div(a.S, sc);
   }
-  dim3 grid((unsigned)blocks, (unsigned)n_frames);
+  if (blocks * n_frames > 2147483647LL)
+    return fail(BBT_EUNSUPPORTED, "grid too large");
+  dim3 grid((unsigned)(blocks * n_frames));
   const size_t smem = C::SMEM_BYTES;
   auto kern = dd_row_kernel<C, PLANAR>;
   if (BBT_SET_SMEM(kern, smem))
@@ -178,10 +181,11 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     // faster than one 128 KB tile); bit 14 of the hint switches that off.
     if (!planar && !((hint >> 14) & 1)) p->half |= 2;
   }
-  p->tw = twiddle_table();
+  p->tw2 = twiddle_table(p->log2n2);
+  p->tw1 = p->log2n1 > 0 ? twiddle_table(p->log2n1) : p->tw2;
   void* d = nullptr;
   int rc = BBT_OK;
-  if (!p->tw) rc = BBT_ENOMEM;
+  if (!p->tw1 || !p->tw2) rc = BBT_ENOMEM;
   if (!rc && dev_alloc(&d, n_chirp * n * sizeof(cf))) rc = BBT_ENOMEM;
   p->chirp = static_cast<cf*>(d);
   d = nullptr;
@@ -306,7 +310,8 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
   a.in = static_cast<const cf*>(in);
   a.out = static_cast<cf*>(out);
   a.work = static_cast<cf*>(work);
-  a.tw = p->tw;
+  a.tw = p->tw2;
+  a.tw1 = p->tw1;
   a.big = BigTwiddle{p->big_lo, p->big_hi};
   a.chirp = p->chirp;
   a.series_map = p->series_map;
@@ -324,6 +329,7 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
   a.out_shift = (p->pad_start + skip) * p->n_series;
   a.scale = (float)(1.0 / (double)p->n);
   a.ahead = sm_count();
+  a.n_frames = (int)n_frames;
   int rc = BBT_EUNSUPPORTED;
   if (p->log2n1 == 0) {
     const bool lanefast = p->n_series > 1;

@@ -117,7 +117,7 @@ int bbt_channelize_power_exec(const void* in, void* out, int64_t n, int64_t m,
   ChanPowArgs a{};
   a.in = static_cast<const cf2*>(in);
   a.out = static_cast<float*>(out);
-  a.tw = twiddle_table();
+  a.tw = twiddle_table(ilog2(n));
   a.M = m;
   a.n_spec = n_spec;
   return run_chanpow<false>(ilog2(n), a, 1, n_spec, as_stream(stream));
@@ -137,7 +137,7 @@ int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
   a.out = static_cast<float*>(sum);
   a.count = static_cast<unsigned long long*>(count);
   a.offsets = reinterpret_cast<const long long*>(offsets);
-  a.tw = twiddle_table();
+  a.tw = twiddle_table(ilog2(n));
   a.M = m;
   a.n_spec = n_spec;
   a.j_first = j_first;
@@ -249,7 +249,7 @@ int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
   a.in = in;
   a.out = static_cast<cf*>(out);
   a.h = static_cast<const float*>(response);
-  a.tw = twiddle_table();
+  a.tw = twiddle_table(ilog2(n));
   a.inner = inner;
   a.n_spec = n_spec;
   a.n_tap = (int)n_tap;

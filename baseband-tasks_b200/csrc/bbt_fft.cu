@@ -44,7 +44,8 @@ struct bbt_fft_plan {
   int kind, direction;
   float scale;
   int log2n, log2n1, log2n2;  // n = n1*n2 when n > kTwiddleTable
-  const cf* tw;
+  const cf* tw;   // roots of unity for n (or n2 of the four-step split)
+  const cf* tw1;  // roots of unity for n1
   cf* big_lo;
   cf* big_hi;
 };
@@ -80,8 +81,9 @@ int bbt_fft_plan_create(bbt_fft_plan** plan, int64_t n, int64_t outer,
   p->log2n = l;
   p->log2n1 = p->log2n2 = 0;
   p->big_lo = p->big_hi = nullptr;
-  p->tw = twiddle_table();
-  if (!p->tw) {
+  p->tw = twiddle_table(l <= kLog2TwiddleTable ? l : (l + 1) / 2);
+  p->tw1 = l <= kLog2TwiddleTable ? p->tw : twiddle_table(l - (l + 1) / 2);
+  if (!p->tw || !p->tw1) {
     delete p;
     return fail(BBT_ENOMEM, "cannot allocate twiddle table");
   }
@@ -125,7 +127,7 @@ int bbt_fft_exec(const bbt_fft_plan* p, const void* in, void* out, void* work,
       (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
   cf* w = static_cast<cf*>(work);
   int rc;
-  FftArgs col{in, w, p->tw, p->outer, n2, inverse, 1.f};
+  FftArgs col{in, w, p->tw1, p->outer, n2, inverse, 1.f};
   if ((rc = run_fft(p->log2n1, BBT_C2C, col, st))) return rc;
   BBT_LAUNCH(twiddle_kernel, dim3(tw_blocks), dim3(256), 0, st, w, n1, n2,
              p->outer, big, inverse);

@@ -29,8 +29,8 @@ inline bbt_stream_t as_stream(void* s) { return static_cast<bbt_stream_t>(s); }
 
 // exp(-2 pi i m / denom), m < count, on the device (computed in float64).
 cf* make_roots(int64_t count, double denom);
-// Per-device table of the kTwiddleTable-th roots of unity.
-const cf* twiddle_table();
+// Per-device table of the 2^log2n-th roots of unity, exp(-2 pi i m / 2^log2n).
+const cf* twiddle_table(int log2n);
 
 inline unsigned grid_for(int64_t total, int threads) {
   return (unsigned)std::max<int64_t>(

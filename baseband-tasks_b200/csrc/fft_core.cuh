@@ -195,8 +195,10 @@ struct Dft<32> {
 };
 
 // ---------------------------------------------------------------------------
-// Twiddle table: exp(-2 pi i m / kTwiddleTable), m < kTwiddleTable; also the
-// largest single-CTA transform.
+// Largest single-CTA transform, and the size of the low-order table of the
+// large-N twiddle W_N^m.  Each block FFT of N points takes the table of the
+// N-th roots of unity exp(-2 pi i m / N), m < N (compact, so that the few
+// entries a stage needs stay in L1).
 constexpr int kLog2TwiddleTable = 14;
 constexpr int kTwiddleTable = 1 << kLog2TwiddleTable;
 
@@ -217,8 +219,9 @@ struct StagePlan {
 
 // Configuration of a block FFT: N points, E elements per thread, THREADS
 // threads per CTA, hence G = THREADS*E/N transforms ("lanes") per CTA.
-template <int LOG2N, int LOG2E_, int THREADS_>
+template <int LOG2N_, int LOG2E_, int THREADS_>
 struct FftCfg {
+  static constexpr int LOG2N = LOG2N_;
   static constexpr int LOG2E = LOG2E_ < LOG2N ? LOG2E_ : LOG2N;
   static constexpr int N = 1 << LOG2N;
   static constexpr int E = 1 << LOG2E;  // elements per thread
@@ -376,7 +379,8 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
 #pragma unroll
     for (int r = 0; r < R; ++r) b[r] = v[q + r * NB];
     if constexpr (LOG2NS > 0)
-      apply_twiddles<R>(b, tw, k << (kLog2TwiddleTable - LOG2NS - LOG2R));
+      // tw is the table of N-th roots of unity: exp(-2 pi i m / N), m < N.
+      apply_twiddles<R>(b, tw, k << (C::LOG2N - LOG2NS - LOG2R));
     Dft<R>::run(b);
     if constexpr ((1 << (LOG2NS + LOG2R)) == C::N) {
 #pragma unroll

@@ -28,7 +28,8 @@ struct DdArgs {
   const cf* in;         // first frame; frame f starts in_frame_stride later
   cf* out;              // valid output of frame f at out + f*out_frame_stride
   cf* work;             // n_frames * N * S scratch
-  const cf* tw;         // kTwiddleTable roots of unity
+  const cf* tw;         // N2-th roots of unity (row FFTs, single-pass frames)
+  const cf* tw1;        // N1-th roots of unity (column FFTs)
   BigTwiddle big;       // W_N^m
   const cf* chirp;      // [n_chirp][N1][N2]
   const int* series_map;  // series -> chirp index
@@ -40,6 +41,7 @@ struct DdArgs {
   long long out_shift;  // (pad_start+skip)*S
   float scale;          // 1/N
   int ahead;            // CTAs resident at a time: L2 prefetch distance
+  int n_frames;         // frames in this launch
 };
 
 // Ask L2 for `rows` runs of `run_bytes` each, `stride_bytes` apart: the tile a
@@ -94,7 +96,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     }
   }
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
-  block_fft<C>(v, t, a.tw, sm);
+  block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
     cf* dst = a.work + frame * a.N * a.S;
     long long step;
@@ -175,7 +177,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     }
   }
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
-  block_fft<C>(v, t, a.tw, sm);
+  block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
     long long flat = (long long)t * n2s + col;
     const long long fstep = (long long)C::T * n2s;
@@ -214,7 +216,10 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   cf* smem = BBT_SMEM(cf);
   const long long n1 = a.N >> a.log2n2;
   const int tid = threadIdx.x;
-  const long long frame = blockIdx.y;
+  // Frames vary fastest over the grid: CTAs that run together share the
+  // chirp rows, which then come from L2 for all but the first frame.
+  const long long frame = blockIdx.x % a.n_frames;
+  const long long xblk = blockIdx.x / a.n_frames;
   int t, g;
   long long k1, s, stride;
   bool valid;
@@ -222,7 +227,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (PLANAR) {
     t = tid % C::T;
     g = tid / C::T;
-    const long long rho = (long long)blockIdx.x * C::G + g;
+    const long long rho = xblk * C::G + g;
     valid = rho < n1 * a.S;
     k1 = rho / a.S;
     s = rho % a.S;
@@ -235,7 +240,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     const int sc = a.S < C::G ? (int)a.S : C::G;
     const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
     const long long chunks = (a.S + sc - 1) / sc;
-    const long long rblk = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const long long rblk = xblk / chunks, chunk = xblk % chunks;
     const int kl = g / sc, sl = g % sc;
     k1 = rblk * rpc + kl;
     s = chunk * sc + sl;
@@ -259,12 +264,9 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
                  : mk(0.f, 0.f);
   {
     // The rows the CTA `ahead` blocks later will load.
-    long long nb = (long long)blockIdx.x + a.ahead, nf = frame;
-    if (nb >= gridDim.x) {
-      nb -= gridDim.x;
-      ++nf;
-    }
-    if (nf < gridDim.y && nb < gridDim.x) {
+    const long long nlin = (long long)blockIdx.x + a.ahead;
+    const long long nb = nlin / a.n_frames, nf = nlin % a.n_frames;
+    if (nlin < gridDim.x) {
       const cf* base2 = a.work + nf * a.N * a.S;
       long long elems = (long long)C::G * C::N;
       if (PLANAR) {
@@ -298,7 +300,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (valid) {
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
-      v[e] = cconj(cmul(v[e], ld_stream(chirp + t + C::T * e)));
+      // Default cache policy: the row is re-read for the other frames.
+      v[e] = cconj(cmul(v[e], ldtw(chirp, t + C::T * e)));
   }
   if (PLANAR) {
     SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};

@@ -19,7 +19,7 @@ namespace bbt {
 struct FftArgs {
   const void* in;
   void* out;
-  const cf* tw;     // exp(-2 pi i m / kTwiddleTable)
+  const cf* tw;     // exp(-2 pi i m / n), m < n
   long long outer;  // number of outer indices
   long long inner;  // number of inner columns
   int inverse;      // 0 forward, 1 backward
