@@ -218,18 +218,75 @@ def run_b200(args):
     def step_resident():
         return run_chain(chain)
 
-    # End to end: pinned host block -> device -> chain -> host.
+    # End to end: pinned host block -> device -> chain -> host.  The block is
+    # copied frame by frame on a copy stream while the chain already works on
+    # the frames that have arrived (through the public API: successive reads
+    # of the output samples whose input is on the device).
     dev_stage = torch.empty_like(dev_in)
     _, chain_e2e = build_chain(w, dev_stage, start)
+    copy_stream = torch.cuda.Stream()
+    d2h_stream = torch.cuda.Stream()
+    n_fr = w['frames']
+    row = host.shape[1:].numel() if host.dim() > 1 else 1
+    pieces = [(0, N)] + [(N + (k - 1) * spf, N + k * spf)
+                         for k in range(1, n_fr)]
+    if folding:
+        reads = None
+    else:
+        # Output samples computable from the first k+1 frames.
+        n_out = chain_e2e.shape[0]
+        edges = np.asarray(chain_e2e._get_offsets(np.arange(n_out + 1)))
+        per_out = w['n_chan']           # upstream samples per spectrum
+        reads = []
+        done = 0
+        for k in range(n_fr):
+            avail = (k + 1) * spf
+            upto = int(np.searchsorted(edges * per_out, avail, side='right')
+                       - 1) if k < n_fr - 1 else n_out
+            upto = max(done, min(upto, n_out))
+            reads.append((done, upto))
+            done = upto
 
     def step_e2e():
         nonlocal out_host
-        dev_stage.copy_(host, non_blocking=True)
-        res = run_chain(chain_e2e)
-        if out_host is None:
-            out_host = torch.empty(res.shape, dtype=res.dtype,
-                                   pin_memory=True)
-        out_host.copy_(res, non_blocking=True)
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)      # previous step is done with the stage
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for a0, a1 in pieces:
+                dev_stage[a0:a1].copy_(host[a0:a1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        def to_host(part, pos):
+            # Copy a finished part back while later frames are still in flight.
+            nonlocal out_host
+            if out_host is None:
+                n_total = chain_e2e.shape[0] if reads is not None \
+                    else part.shape[0]
+                out_host = torch.empty((n_total,) + tuple(part.shape[1:]),
+                                       dtype=part.dtype, pin_memory=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            d2h_stream.wait_event(ev)
+            with torch.cuda.stream(d2h_stream):
+                out_host[pos:pos + part.shape[0]].copy_(part,
+                                                        non_blocking=True)
+                part.record_stream(d2h_stream)
+
+        if reads is None:
+            main.wait_event(events[-1])
+            res = run_chain(chain_e2e)
+            to_host(res, 0)
+        else:
+            chain_e2e.seek(0)
+            res = None
+            for k, (b0, b1) in enumerate(reads):
+                main.wait_event(events[k])
+                if b1 > b0:
+                    res = chain_e2e.read_device(b1 - b0)
+                    to_host(res, b0)
+        main.wait_stream(d2h_stream)
         return res
 
     def barrier():
@@ -264,7 +321,7 @@ def run_b200(args):
     clocks = clocks_summary(sampler)
 
     for _ in range(2):
-        step_e2e()
+        res_e2e = step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
     # Per-kernel durations, CUDA events on the launching stream.
