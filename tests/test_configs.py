@@ -1,0 +1,207 @@
+"""The BASELINE.json configurations through the public Task API on the B200,
+against the oracle (full size where the oracle finishes in seconds, otherwise
+reduced in duration only) and through size-independent properties.
+"""
+import numpy as np
+import pytest
+
+import bbt_oracle as orc
+
+from test_kernels import assert_voltage, assert_power, cnoise, rms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def bt():
+    import baseband_tasks_b200 as pkg
+    return pkg
+
+
+def t0(bt):
+    return bt.Time(1289567655)
+
+
+def test_c1_dedisperse_full_size(bt):
+    """configs[0]: 1-ch complex64 16 MHz, 2^22 samples, DM=26.8, N=2^21."""
+    n, rate, freq, dm, spf = 1 << 22, 16e6, 400e6, 26.8, 1206812
+    src = bt.NoiseGenerator((n,), t0(bt), rate, samples_per_frame=1 << 20,
+                            dtype='c8', seed=1234568, frequency=freq,
+                            sideband=1)
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    assert dd._ih_samples_per_frame == 1 << 21
+    assert (dd._pad_start, dd._pad_end) == (431817, 458523)
+    assert dd.shape == (3303964,)
+    x = orc.noise_stream(1234568, n, 1 << 20)
+    op = orc.DispersePlan(-dm, freq / 1e6, 1, rate / 1e6, True, n, 1 << 20,
+                          samples_per_frame=spf, fast_len=orc.next_pow2)
+    want = orc.disperse(x, op)            # 3 frames, the last re-anchored
+    got = dd.read()
+    assert_voltage(got, want)
+    # In double precision the oracle differs from itself by about as much.
+    dd.seek(2 * spf - 5)
+    assert_voltage(dd.read(10), want[2 * spf - 5:2 * spf + 5])
+
+
+@pytest.mark.parametrize('step', [1e-3, 8])
+def test_c2_chain(bt, step):
+    """configs[1], 3 frames: 8ch x 2pol -> Dedisperse(100) -> Channelize(1024)
+    -> Power -> Integrate(1 ms, or 8 spectra for the tie-free check)."""
+    rate, dm, log2n = 8e6, 100., 20
+    freq = (1372e6 + 8e6 * np.arange(8)).reshape(8, 1)
+    N = 1 << log2n
+    pad = 74847 + 80161
+    spf = N - pad
+    n = 2 * spf + N
+    shape = (8, 2)
+    src = bt.NoiseGenerator((n,) + shape, t0(bt), rate,
+                            samples_per_frame=1 << 18, dtype='c8',
+                            seed=1234569, frequency=freq, sideband=1,
+                            polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    assert (dd._pad_start, dd._pad_end) == (74847, 80161)
+    assert dd._ih_samples_per_frame == N and dd.shape[0] == 3 * spf
+    it = bt.Integrate(bt.Power(bt.Channelize(dd, 1024)), step, average=False)
+    assert it._fused == 'chanpow'
+    got = it.read()
+    x = orc.noise_stream(1234569, n, 1 << 18, shape)
+    op = orc.DispersePlan(-dm, freq / 1e6, 1, rate / 1e6, True, n, 1 << 18,
+                          shape, samples_per_frame=spf,
+                          fast_len=orc.next_pow2)
+    y = orc.disperse(x, op)
+    dd.seek(spf - 100)
+    assert_voltage(dd.read(200), y[spf - 100:spf + 100])
+    power = orc.power(orc.channelize(y, 1024), axis=-1)
+    ip = orc.IntegratePlan(power.shape[0], rate / 1024, step)
+    offsets = ip.offsets(np.arange(ip.n_out + 1))
+    want, count = orc.integrate(power, offsets)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got['count'][:, 0, 0, 0], count.ravel())
+    assert_power(got['data'], want)
+    if step == 8:
+        assert np.all(count == 8)
+    else:
+        assert set(np.unique(count)) == {7, 8}
+
+
+def test_c3_pfb_dedisperse_power(bt):
+    """configs[2], reduced in duration: real 8-bit-valued 800 MS/s, 2 pol ->
+    4-tap 1024(+1)-channel PFB -> per-channel Dedisperse -> Power."""
+    n_chan_in, n_tap = 2048, 4
+    n_spec_in = 2200
+    n = n_spec_in * n_chan_in
+    rate = 800e6
+    rng = np.random.default_rng(1234570)
+    x = np.clip(np.round(rng.normal(size=(n, 2)) * 20), -127, 127).astype('f4')
+    src = bt.ArrayStream(x, t0(bt), rate, samples_per_frame=1 << 16,
+                         frequency=800e6, sideband=-1,
+                         polarization=np.array(['X', 'Y']))
+    response = bt.sinc_hamming(n_tap, n_chan_in)
+    pfb = bt.PolyphaseFilterBank(src, response)
+    assert pfb.shape[1:] == (1025, 2) and pfb.sample_rate == rate / 2048
+    dm = 10.
+    dd = bt.Dedisperse(pfb, dm, reference_frequency=pfb.frequency)
+    pw = bt.Power(dd)
+    want_pfb = orc.pfb(x.astype('f8'), response, ih_samples_per_frame=1 << 16)
+    assert pfb.shape == want_pfb.shape
+    assert_voltage(pfb.read(), want_pfb.astype('c8'), tol=2e-5)
+    freq = orc.channelize_frequency(800., -1, 2048, rate / 1e6, True, 1)
+    op = orc.DispersePlan(-dm, freq, -1, rate / 2048 / 1e6, True,
+                          want_pfb.shape[0], pfb.samples_per_frame, (1025, 2),
+                          reference_frequency_mhz=freq,
+                          fast_len=orc.next_pow2)
+    assert (dd._pad_start, dd._pad_end, dd._ih_samples_per_frame) == (
+        op.pad_start, op.pad_end, op.N)
+    y = orc.disperse(want_pfb.astype('c8'), op)
+    assert_voltage(dd.read(), y, tol=3e-5)
+    assert_power(pw.read(), orc.power(y, axis=-1), tol=1e-4)
+
+
+def test_c4_frame_full_size(bt):
+    """configs[3]: 512 MHz dual-pol, DM=1000, 2^24-point frames: one and a
+    half frames against the oracle, plus linearity at full size."""
+    rate, freq, dm = 512e6, 8192e6, 1000.
+    N = 1 << 24
+    pad_start, pad_end = 1889551, 2075345
+    spf = N - pad_start - pad_end
+    n = N + spf // 2
+    rng = np.random.default_rng(1234571)
+    x = cnoise(rng, (n, 2))
+    src = bt.ArrayStream(x, t0(bt), rate, samples_per_frame=1 << 20,
+                         frequency=freq, sideband=1,
+                         polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    assert (dd._pad_start, dd._pad_end) == (pad_start, pad_end)
+    assert dd._ih_samples_per_frame == N
+    got = dd.read()
+    op = orc.DispersePlan(-dm, freq / 1e6, 1, rate / 1e6, True, n, 1 << 20,
+                          (2,), samples_per_frame=spf,
+                          fast_len=orc.next_pow2)
+    want = orc.disperse(x, op)
+    assert got.shape == want.shape == (n - pad_start - pad_end, 2)
+    assert_voltage(got, want)
+    # Linearity: D(a x + b x') = a D(x) + b D(x').
+    x2 = cnoise(rng, (n, 2))
+    a, b = 0.75 - 0.5j, -1.25 + 0.3j
+    mix = bt.ArrayStream((a * x + b * x2).astype('c8'), t0(bt), rate,
+                         frequency=freq, sideband=1)
+    other = bt.ArrayStream(x2, t0(bt), rate, frequency=freq, sideband=1)
+    d_mix = bt.Dedisperse(mix, dm, samples_per_frame=spf).read(spf)
+    d_other = bt.Dedisperse(other, dm, samples_per_frame=spf).read(spf)
+    assert_voltage(d_mix, a * got[:spf] + b * d_other, tol=2e-5)
+    # Energy: the chirp is a pure phase, so a whole frame keeps its power
+    # (valid part against the matching part of the circular result).
+    assert abs(rms(got[:spf]) / rms(x[pad_start:pad_start + spf]) - 1) < 1e-3
+
+
+def test_c5_fold_full_frame(bt):
+    """configs[4]: Dedisperse -> Power -> Fold(512, polynomial) over one
+    2^24-point frame: counts bit-exact, sums to 1e-5."""
+    rate, freq, dm = 512e6, 8192e6, 1000.
+    N = 1 << 24
+    spf = N - 1889551 - 2075345
+    rng = np.random.default_rng(1234572)
+    x = cnoise(rng, (N, 2))
+    src = bt.ArrayStream(x, t0(bt), rate, frequency=freq, sideband=1,
+                         polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    poly = bt.PolynomialPhase([0.25, 29.946923, -3.77535e-10 / 2.], t0(bt))
+    # A pulsar this slow fills 2 of 512 bins in 25 ms: spin it up so that
+    # all bins are visited and bin edges are crossed ~10^5 times.
+    fast = bt.PolynomialPhase([0.25, 29.946923e3, -3.77535e-4 / 2.], t0(bt))
+    for phase in (poly, fast):
+        fold = bt.Fold(bt.Power(dd), 512, phase, average=False)
+        assert fold._fused == 'power'
+        got = fold.read()
+        dd.seek(0)
+        y = dd.read()
+        power = orc.power(y, axis=-1)
+        i_ref = phase.i_ref(dd.start_time, rate)
+        phases = phase.of_index(np.arange(spf), i_ref, rate)
+        pbin = ((phases % 1.) * 512).astype(int)
+        count = np.bincount(pbin, minlength=512)
+        np.testing.assert_array_equal(got['count'][0, :, 0], count)
+        assert got['count'].sum() == spf * 4
+        for c in range(4):
+            want = np.bincount(pbin, weights=power[:, c].astype('f8'),
+                               minlength=512)
+            np.testing.assert_allclose(got['data'][0, :, c], want, rtol=2e-5,
+                                       atol=2e-5 * np.abs(want).max())
+
+
+def test_empty_and_edge_reads(bt):
+    """Zero-length reads, reads to exactly the end, and one past it."""
+    x = cnoise(np.random.default_rng(3), (3 * 4096, 2))
+    src = bt.ArrayStream(x, t0(bt), 1e6, frequency=300e6, sideband=1,
+                         polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, 3., samples_per_frame=4096 - 923)
+    assert dd.read(0).shape == (0, 2)
+    dd.seek(0, 2)
+    assert dd.read().shape == (0, 2)
+    with pytest.raises(EOFError):
+        dd.read(1)
+    pw = bt.Power(bt.Channelize(dd, 64))
+    pw.seek(-1, 2)
+    assert pw.read().shape == (1, 64, 4)
+    with pytest.raises(AssertionError):
+        bt.Channelize(dd, 1 << 15)     # frame larger than the stream
