@@ -50,10 +50,10 @@ _SIGNATURES = {
                                           c_int64, c_int64, c_void_p]),
     'bbt_channelize_power_integrate_exec': (c_int, [
         c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
-        c_int64, c_void_p, c_void_p, c_void_p]),
+        c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     'bbt_integrate_exec': (c_int, [c_void_p, c_int64, c_int64, c_int64,
                                    c_void_p, c_int64, c_int64, c_void_p,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_int, c_void_p]),
     'bbt_fold_exec': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64,
                               c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                               POINTER(c_double), c_int, c_double, c_double,

@@ -1,4 +1,6 @@
 // C-ABI implementation (see include/bbt_b200.h): coherent (de)dispersion.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels_dedisperse.cuh"
 
@@ -11,6 +13,7 @@ struct bbt_dedisperse_plan {
   int col_e32;     // 32 elements per thread in short column FFTs
   int row16;       // 16 elements per thread in the row FFTs
   int half;        // 256-thread CTAs, half-size tiles
+  int col16;       // 16 values per thread, 1024 threads, in column passes
   const cf* tw1;   // roots of unity for the column FFTs (n1)
   const cf* tw2;   // for the row FFTs (n2), or the whole single-pass frame
   cf* big_lo;
@@ -30,16 +33,22 @@ struct ColCfg {
   static constexpr int LOG2E = L1 <= 4 ? L1 : ((L1 <= 8 && !E32) ? 4 : 5);
   using type = FftCfg<L1, LOG2E, HALF ? kColThreads / 2 : kColThreads>;
 };
+// Experimental: 16 values per thread in 1024-thread CTAs (same tile).
+template <int L1>
+struct ColCfg16 {
+  using type = FftCfg<L1, (L1 < 4 ? L1 : 4), 1024>;
+};
 
 int col_lanes(int l1, bool e32) {
   const int log2e = l1 <= 4 ? l1 : ((l1 <= 8 && !e32) ? 4 : 5);
   return kColThreads >> (l1 - log2e);
 }
 
-template <int L1, bool E32, bool HALF = false>
+template <int L1, bool E32, bool HALF = false, bool C16 = false>
 int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
                   bbt_stream_t st) {
-  using C = typename ColCfg<L1, E32, HALF>::type;
+  using C = typename std::conditional<C16, typename ColCfg16<L1>::type,
+                                      typename ColCfg<L1, E32, HALF>::type>::type;
   DdArgs a = a0;
   if (HALF) a.ahead *= 2;
   const int64_t cols = (a.N >> L1) * a.S;
@@ -63,11 +72,15 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   if (HALF) a.ahead *= 2;
   const int64_t n1 = a.N >> L2;
   int64_t blocks;
+  a.row_sc = a.row_rpc = a.row_chunks = 1;
   if (PLANAR) {
     blocks = ceil_div(n1 * a.S, C::G);
   } else {
     const int sc = a.S < C::G ? (int)a.S : C::G;
     const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
+    a.row_sc = sc;
+    a.row_rpc = rpc;
+    a.row_chunks = (int)ceil_div(a.S, sc);
     blocks = ceil_div(n1, rpc) * ceil_div(a.S, sc);
   }
   if (blocks * n_frames > 2147483647LL)
@@ -145,6 +158,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->col_e32 = (hint >> 10) & 1;
   p->row16 = (hint >> 11) & 1;
   p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
+  p->col16 = (hint >> 15) & 1;
   const int hint_l1 = hint & 0xff;
   const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;
   if (l <= kLog2TwiddleTable && (n_series == 1 || l <= 10) && !hint_l1) {
@@ -343,8 +357,10 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
   if (!work) return fail(BBT_EINVAL, "dedispersion needs a work buffer");
   const bool e32 = p->col_e32;
   const bool hcol = p->half & 1, hrow = p->half & 2;
+  const bool c16 = p->col16 && p->log2n1 >= 9;
 #define F(L)                                                              \
-  rc = hcol ? launch_dd_col<L, false, true>(false, a, n_frames, st)       \
+  rc = c16 ? launch_dd_col<L, false, false, true>(false, a, n_frames, st) \
+       : hcol ? launch_dd_col<L, false, true>(false, a, n_frames, st)     \
             : (e32 ? launch_dd_col<L, true>(false, a, n_frames, st)       \
                    : launch_dd_col<L, false>(false, a, n_frames, st))
   BBT_FOR_LOG2(p->log2n1, F)
@@ -367,7 +383,8 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
   if (rc) return rc;
   rc = BBT_EUNSUPPORTED;
 #define F(L)                                                              \
-  rc = hcol ? launch_dd_col<L, false, true>(true, a, n_frames, st)        \
+  rc = c16 ? launch_dd_col<L, false, false, true>(true, a, n_frames, st)  \
+       : hcol ? launch_dd_col<L, false, true>(true, a, n_frames, st)      \
             : (e32 ? launch_dd_col<L, true>(true, a, n_frames, st)        \
                    : launch_dd_col<L, false>(true, a, n_frames, st))
   BBT_FOR_LOG2(p->log2n1, F)

@@ -49,7 +49,7 @@ struct ChanCfg {
   using type = FftCfg<L, LOG2E, THREADS>;
 };
 
-template <class C, bool INTEGRATE>
+template <class C, bool INTEGRATE, int MINB = 1>
 int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st);
 
@@ -66,6 +66,15 @@ int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
     if (g_chan_variant == 3)
       return launch_chanpow_cfg<FftCfg<10, 3, 512>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
+    if (g_chan_variant == 5)
+      return launch_chanpow_cfg<FftCfg<10, 5, 512>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
+    if (g_chan_variant == 6)
+      return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE, 2>(
+          a, n_bins, max_width, st);
+    if (g_chan_variant == 0 && !INTEGRATE)
+      return launch_chanpow_cfg<FftCfg<10, 5, 512>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
     if (g_chan_variant == 0 || g_chan_variant == 4)
       return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
@@ -74,7 +83,7 @@ int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
       a, n_bins, max_width, st);
 }
 
-template <class C, bool INTEGRATE>
+template <class C, bool INTEGRATE, int MINB>
 int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st) {
   constexpr int64_t units = C::G / 2;  // (sub-stream, m) pairs per CTA
@@ -82,12 +91,13 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
   const int64_t want = (int64_t)sm_count() * 4 * units;
   int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));
   if (msub > max_width) msub = max_width;
-  if (msub < 1) msub = 1;
+  // In-kernel averaging divides every partial sum: keep one per bin.
+  if (msub < 1 || (INTEGRATE && a.average)) msub = 1;
   a.msub = msub;
   const int64_t blocks = ceil_div(msub * a.M, units);
   dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
   const size_t smem = C::SMEM_BYTES;
-  auto kern = chanpow_kernel<C, INTEGRATE>;
+  auto kern = chanpow_kernel<C, INTEGRATE, MINB>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
   prof_next_name = INTEGRATE ? "chanpow_integrate" : "chanpow";
@@ -127,7 +137,8 @@ int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
                                         int64_t n_spec, int64_t j_first,
                                         const int64_t* offsets,
                                         int64_t b_first, int64_t n_bins,
-                                        void* sum, void* count, void* stream) {
+                                        void* sum, void* count, int average,
+                                        void* stream) {
   if (!in || !sum || !count || !offsets) return fail(BBT_EINVAL, "null argument");
   if (!is_pow2(n) || n < 2 || m < 1) return fail(BBT_EUNSUPPORTED, "bad channelizer shape");
   if (n_spec <= 0 || n_bins <= 0) return BBT_OK;
@@ -142,6 +153,7 @@ int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
   a.n_spec = n_spec;
   a.j_first = j_first;
   a.b_first = b_first;
+  a.average = average;
   return run_chanpow<true>(ilog2(n), a, n_bins,
                            std::max<int64_t>(1, ceil_div(n_spec, n_bins)),
                            as_stream(stream));
@@ -150,7 +162,7 @@ int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
 int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
                        int64_t i_first, const int64_t* offsets,
                        int64_t b_first, int64_t n_bins, void* sum, void* count,
-                       void* stream) {
+                       int average, void* stream) {
   if (!in || !sum || !count || !offsets) return fail(BBT_EINVAL, "null argument");
   if (n <= 0 || n_bins <= 0 || inner <= 0) return BBT_OK;
   if (n_bins > 65535) return fail(BBT_EUNSUPPORTED, "too many bins per call");
@@ -163,9 +175,11 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
   a.n = n;
   a.i_first = i_first;
   a.b_first = b_first;
+  a.average = average;
   const int64_t want = (int64_t)sm_count() * 2048;
   int64_t msub = ceil_div(want, inner * n_bins);
   msub = std::max<int64_t>(1, std::min<int64_t>(msub, ceil_div(n, n_bins)));
+  if (average) msub = 1;  // one partial sum per bin and call
   a.msub = msub;
   dim3 grid((unsigned)ceil_div(msub * inner, 256), (unsigned)n_bins);
   BBT_LAUNCH(integrate_kernel, grid, dim3(256), 0, as_stream(stream), a);

@@ -42,19 +42,25 @@ struct DdArgs {
   float scale;          // 1/N
   int ahead;            // CTAs resident at a time: L2 prefetch distance
   int n_frames;         // frames in this launch
+  // Interleaved row tiles (set by the launcher): series per tile, rows per
+  // tile, tiles per row.
+  int row_sc, row_rpc, row_chunks;
 };
 
 // Ask L2 for `rows` runs of `run_bytes` each, `stride_bytes` apart: the tile a
 // CTA launched `ahead` blocks later will load, so that its DRAM fetch overlaps
 // this CTA's arithmetic.
-BBT_HD void prefetch_tile(const cf* base, long long rows, long long stride,
+BBT_HD void prefetch_tile(const cf* base, int rows, long long stride,
                           int run_elems, int tid, int nthreads) {
   const int lines = (run_elems * 8 + 127) / 128;
-  const long long total = rows * lines;
-  for (long long i = tid; i < total; i += nthreads) {
-    const long long r = i / lines;
-    const int l = (int)(i % lines);
-    prefetch_l2(base + r * stride + l * 16);
+  if (lines == 1) {
+    for (int r = tid; r < rows; r += nthreads) prefetch_l2(base + r * stride);
+  } else {
+    const int total = rows * lines;
+    for (int i = tid; i < total; i += nthreads) {
+      const int r = i / lines, l = i - r * lines;
+      prefetch_l2(base + r * stride + l * 16);
+    }
   }
 }
 
@@ -101,7 +107,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     cf* dst = a.work + frame * a.N * a.S;
     long long step;
     if (a.planar) {
-      const long long n2 = col / a.S, s = col % a.S;
+      const unsigned n2 = (unsigned)col / (unsigned)a.S;
+      const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
       const long long N2 = a.N >> a.log2n1;
       dst += s * N2 + n2;
       step = a.S * N2;
@@ -133,7 +140,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   const cf* src = a.work + frame * a.N * a.S;
   long long step;
   if (a.planar) {
-    const long long n2 = col / a.S, s = col % a.S;
+    const unsigned n2 = (unsigned)col / (unsigned)a.S;
+    const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
     const long long N2 = a.N >> a.log2n1;
     src += s * N2 + n2;
     step = a.S * N2;
@@ -163,7 +171,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       if (a.planar) {
         // Runs of the tile's n2 values, one per (k1, s).
         const long long N2 = a.N >> a.log2n1;
-        const long long n20 = c0 / a.S, s0 = c0 % a.S;
+        const unsigned n20 = (unsigned)c0 / (unsigned)a.S;
+        const unsigned s0 = (unsigned)c0 - n20 * (unsigned)a.S;
         const int ns = a.S < C::G ? (int)a.S : C::G;       // series in tile
         const int tn = a.S < C::G ? C::G / (int)a.S : 1;   // n2 per series
         for (int si = 0; si < ns; ++si)
@@ -218,8 +227,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   const int tid = threadIdx.x;
   // Frames vary fastest over the grid: CTAs that run together share the
   // chirp rows, which then come from L2 for all but the first frame.
-  const long long frame = blockIdx.x % a.n_frames;
-  const long long xblk = blockIdx.x / a.n_frames;
+  const unsigned xblk = blockIdx.x / (unsigned)a.n_frames;
+  const long long frame = blockIdx.x - xblk * (unsigned)a.n_frames;
   int t, g;
   long long k1, s, stride;
   bool valid;
@@ -227,21 +236,19 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (PLANAR) {
     t = tid % C::T;
     g = tid / C::T;
-    const long long rho = xblk * C::G + g;
-    valid = rho < n1 * a.S;
-    k1 = rho / a.S;
-    s = rho % a.S;
-    row += rho * C::N;
+    const unsigned rho = xblk * C::G + g;
+    valid = rho < (unsigned)(n1 * a.S);
+    k1 = rho / (unsigned)a.S;
+    s = rho - (unsigned)k1 * (unsigned)a.S;
+    row += (long long)rho * C::N;
     stride = 1;
   } else {
     g = tid % C::G;
     t = tid / C::G;
-    // Series per CTA chunk, rows per CTA.
-    const int sc = a.S < C::G ? (int)a.S : C::G;
-    const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
-    const long long chunks = (a.S + sc - 1) / sc;
-    const long long rblk = xblk / chunks, chunk = xblk % chunks;
-    const int kl = g / sc, sl = g % sc;
+    // Series per tile, rows per tile, tiles per row (from the launcher).
+    const unsigned sc = a.row_sc, rpc = a.row_rpc, chunks = a.row_chunks;
+    const unsigned rblk = xblk / chunks, chunk = xblk - rblk * chunks;
+    const unsigned kl = (unsigned)g / sc, sl = (unsigned)g - kl * sc;
     k1 = rblk * rpc + kl;
     s = chunk * sc + sl;
     valid = kl < rpc && k1 < n1 && s < a.S;
@@ -264,20 +271,18 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
                  : mk(0.f, 0.f);
   {
     // The rows the CTA `ahead` blocks later will load.
-    const long long nlin = (long long)blockIdx.x + a.ahead;
-    const long long nb = nlin / a.n_frames, nf = nlin % a.n_frames;
+    const unsigned nlin = blockIdx.x + (unsigned)a.ahead;
+    const unsigned nb = nlin / (unsigned)a.n_frames;
+    const unsigned nf = nlin - nb * (unsigned)a.n_frames;
     if (nlin < gridDim.x) {
       const cf* base2 = a.work + nf * a.N * a.S;
       long long elems = (long long)C::G * C::N;
       if (PLANAR) {
-        base2 += nb * C::G * C::N;
+        base2 += (long long)nb * C::G * C::N;
       } else {
-        const int sc = a.S < C::G ? (int)a.S : C::G;
-        const int rpc = (C::G % sc == 0) ? C::G / sc : 1;
-        const long long chunks = (a.S + sc - 1) / sc;
-        if (chunks == 1) {
-          base2 += (nb * rpc) * C::N * a.S;
-          elems = (long long)rpc * C::N * a.S;
+        if (a.row_chunks == 1) {
+          base2 += ((long long)nb * a.row_rpc) * C::N * a.S;
+          elems = (long long)a.row_rpc * C::N * a.S;
         } else {
           elems = 0;  // strided chunks: leave to the hardware
         }

@@ -71,6 +71,7 @@ struct ChanPowArgs {
   long long j_first;      // absolute index of the first spectrum in `in`
   long long b_first;      // first bin handled (blockIdx.y = 0)
   long long msub;         // concurrent spectrum sub-streams per bin
+  int average;            // scale sums by 1 / (bin width) on the way out
 };
 
 // Lanes of a tile are (unit, polarization) pairs, polarization fastest, where
@@ -79,8 +80,8 @@ struct ChanPowArgs {
 // bytes per time sample.  After the transform the two threads holding X and Y
 // of a channel swap half of their values (one shuffle per value), and each
 // forms all four products for every other channel.
-template <class C, bool INTEGRATE>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
+template <class C, bool INTEGRATE, int MINB = 1>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, MINB) chanpow_kernel(ChanPowArgs a) {
   static_assert(C::G % 2 == 0 && C::E % 2 == 0, "pairs of lanes and values");
   cf* smem = BBT_SMEM(cf);
   const int tid = threadIdx.x;
@@ -156,14 +157,18 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
   }
   if (INTEGRATE) {
     if (lane_ok && hi > lo) {
+      // Averages: every partial sum is divided by the full width of its bin
+      // (known from the offsets table), so no separate division pass is needed.
+      const float w =
+          a.average ? (float)(a.offsets[b + 1] - a.offsets[b]) : 1.f;
 #pragma unroll
       for (int i = 0; i < C::E / 2; ++i) {
         const int k = t + C::T * (2 * i + p);
         float* o = a.out + ((b * C::N + k) * a.M + m) * 4;
-        atomic_add(o + 0, acc[i].x);
-        atomic_add(o + 1, acc[i].y);
-        atomic_add(o + 2, acc[i].z);
-        atomic_add(o + 3, acc[i].w);
+        atomic_add(o + 0, acc[i].x / w);
+        atomic_add(o + 1, acc[i].y / w);
+        atomic_add(o + 2, acc[i].z / w);
+        atomic_add(o + 3, acc[i].w / w);
       }
     }
     if (tid == 0 && blockIdx.x == 0 && hi > lo)
@@ -181,6 +186,7 @@ struct IntegrateArgs {
   unsigned long long* count;
   const long long* offsets;
   long long inner, n, i_first, b_first, msub;
+  int average;
 };
 
 BBT_GLOBAL void integrate_kernel(IntegrateArgs a) {
@@ -195,6 +201,7 @@ BBT_GLOBAL void integrate_kernel(IntegrateArgs a) {
   if (sub >= a.msub) return;
   float acc = 0.f;
   for (long long i = lo + sub; i < hi; i += a.msub) acc += a.in[i * a.inner + c];
+  if (a.average) acc /= (float)(a.offsets[b + 1] - a.offsets[b]);
   atomic_add(a.sum + b * a.inner + c, acc);
 }
 

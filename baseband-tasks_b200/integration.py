@@ -29,6 +29,8 @@ from .functions import Power
 __all__ = ['Integrate', 'Fold', 'PolynomialPhase']
 
 _MAX_BINS_PER_LAUNCH = 32768
+# Fewest output values for which averages are formed inside the kernels.
+_AVERAGE_IN_KERNEL_MIN = 262144
 
 
 class PolynomialPhase:
@@ -284,7 +286,20 @@ class Integrate(BaseTaskBase):
             inner *= 2
         sums = B.zeros((n_sample, inner), np.float32)
         count = B.zeros((n_sample,), np.int64)
+        # Averages are formed inside the kernels (each contribution divided
+        # by the width of its bin, known from the offsets).
+        # Only with enough bins to fill the GPU at one partial sum per bin;
+        # otherwise bins are split over many CTAs and divided afterwards.
+        parallel = (n_sample * self._chan_m * 128 if self._fused == 'chanpow'
+                    else n_sample * inner)
+        self._average_in_kernel = (self.average
+                                   and parallel >= _AVERAGE_IN_KERNEL_MIN
+                                   and not getattr(self, '_raw_sums', False))
         self._accumulate(offsets, sums, count)
+        if self._average_in_kernel:
+            empty = np.flatnonzero(np.diff(offsets) == 0)
+            if len(empty):      # no samples: NaN, as 0 / 0 gives
+                sums[B.as_device(empty)] = float('nan')
         return self._finish(sums, count, (n_sample,) + self.sample_shape)
 
     def _finish(self, sums, count, shape):
@@ -295,10 +310,14 @@ class Integrate(BaseTaskBase):
         ih_dtype = np.dtype(self.ih.dtype)
         single = np.complex64 if ih_dtype.kind == 'c' else np.float32
         if self.average:
-            out = B.empty(sums.shape, np.float32)
-            lib.check(lib.bbt_average_exec(
-                B.ptr(sums), B.ptr(count), B.ptr(out), count.numel(),
-                sums.numel() // max(count.numel(), 1), _cabi.stream_ptr()))
+            if getattr(self, '_average_in_kernel', False):
+                out = sums
+            else:
+                out = B.empty(sums.shape, np.float32)
+                lib.check(lib.bbt_average_exec(
+                    B.ptr(sums), B.ptr(count), B.ptr(out), count.numel(),
+                    sums.numel() // max(count.numel(), 1),
+                    _cabi.stream_ptr()))
             out = _as_dtype(out, single).reshape(shape)
             if self.dtype != np.dtype(single):
                 out = out.to(B.torch_dtype(self.dtype))
@@ -344,12 +363,13 @@ class Integrate(BaseTaskBase):
                     lib.check(lib.bbt_channelize_power_integrate_exec(
                         B.ptr(x), self._chan_n, self._chan_m, n, pos,
                         B.ptr(d_off), bb, nb, B.ptr(sums), B.ptr(count),
-                        _cabi.stream_ptr()))
+                        int(self._average_in_kernel), _cabi.stream_ptr()))
                 else:
                     x = _as_float32(x, src.dtype)
                     lib.check(lib.bbt_integrate_exec(
                         B.ptr(x), n, sums.shape[1], pos, B.ptr(d_off), bb,
-                        nb, B.ptr(sums), B.ptr(count), _cabi.stream_ptr()))
+                        nb, B.ptr(sums), B.ptr(count),
+                        int(self._average_in_kernel), _cabi.stream_ptr()))
             pos = nxt
         assert n_bins == count.shape[0]
 

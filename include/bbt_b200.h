@@ -108,19 +108,23 @@ int bbt_channelize_power_exec(const void* in, void* out, int64_t n, int64_t m,
 /* ... -> Integrate: additionally integration.py:273-303.  offsets (device,
  * int64) are absolute bin edges in spectra; bins b_first .. b_first+n_bins-1
  * are accumulated (+=) into sum[bin][n][m][4] (float32) and count[bin]
- * (int64) for the part that overlaps spectra [j_first, j_first + n_spec). */
+ * (int64) for the part that overlaps spectra [j_first, j_first + n_spec).
+ * With average != 0 every contribution is divided by the full width of its
+ * bin, offsets[bin+1] - offsets[bin], so that sum ends up holding the averages
+ * (the division of integration.py:268-269) without a separate pass. */
 int bbt_channelize_power_integrate_exec(const void* in, int64_t n, int64_t m,
                                         int64_t n_spec, int64_t j_first,
                                         const int64_t* offsets,
                                         int64_t b_first, int64_t n_bins,
-                                        void* sum, void* count, void* stream);
+                                        void* sum, void* count, int average,
+                                        void* stream);
 
 /* ---- Integrate: replaces Integrate._integrate (integration.py:273-303) for
  * float32 input [n][inner]; same offsets/accumulate convention as above. */
 int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
                        int64_t i_first, const int64_t* offsets,
                        int64_t b_first, int64_t n_bins, void* sum, void* count,
-                       void* stream);
+                       int average, void* stream);
 
 /* ---- Fold: replaces Fold._integrate (integration.py:380-395).  Time bin b
  * covers absolute samples [lo[b], hi[b]) (device int64; the host applies the

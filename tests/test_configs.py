@@ -78,6 +78,8 @@ def test_c2_chain(bt, step):
     assert got.shape == want.shape
     np.testing.assert_array_equal(got['count'][:, 0, 0, 0], count.ravel())
     assert_power(got['data'], want)
+    avg = bt.Integrate(it.ih, step).read()
+    assert_power(avg, want / count)
     if step == 8:
         assert np.all(count == 8)
     else:

@@ -364,7 +364,7 @@ def test_channelize_power_integrate(backend, n, m, n_spec, ratio):
         ptr = ctypes.c_void_p(backend.ptr(d_in).value + j0 * n * m * 2 * 8)
         backend.lib.check(backend.lib.bbt_channelize_power_integrate_exec(
             ptr, n, m, j1 - j0, j0, backend.ptr(d_off), 0, n_bins,
-            backend.ptr(d_sum), backend.ptr(d_cnt), backend.stream))
+            backend.ptr(d_sum), backend.ptr(d_cnt), 0, backend.stream))
     backend.sync()
     np.testing.assert_array_equal(backend.to_host(d_cnt), wcount.ravel())
     assert_power(backend.to_host(d_sum), want)
@@ -389,7 +389,7 @@ def test_integrate(backend, n, inner, ratio):
         ptr = ctypes.c_void_p(backend.ptr(d_in).value + i0 * inner * 4)
         backend.lib.check(backend.lib.bbt_integrate_exec(
             ptr, i1 - i0, inner, i0, backend.ptr(d_off), 0, n_bins,
-            backend.ptr(d_sum), backend.ptr(d_cnt), backend.stream))
+            backend.ptr(d_sum), backend.ptr(d_cnt), 0, backend.stream))
     backend.sync()
     np.testing.assert_array_equal(backend.to_host(d_cnt), wcount.ravel())
     assert_power(backend.to_host(d_sum), want)

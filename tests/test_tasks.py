@@ -263,6 +263,17 @@ def test_chain_dedisperse_channelize_power_integrate(bt, device_input):
     assert_power(res['data'], want)
     avg = bt.Integrate(pw, step).read()
     assert_power(avg, want / wcount)
+    # The same with the averages formed inside the kernels.
+    from baseband_tasks_b200 import integration
+    saved = integration._AVERAGE_IN_KERNEL_MIN
+    integration._AVERAGE_IN_KERNEL_MIN = 0
+    try:
+        assert_power(bt.Integrate(pw, step).read(), want / wcount)
+        unfused = bt.Integrate(pw, step)
+        unfused._fused, unfused._src, unfused._src_ratio = None, pw, 1
+        assert_power(unfused.read(), want / wcount)
+    finally:
+        integration._AVERAGE_IN_KERNEL_MIN = saved
     # Unfused path gives the same.
     it2 = bt.Integrate(pw, step, average=False)
     it2._fused, it2._src, it2._src_ratio = None, pw, 1
@@ -581,3 +592,26 @@ def test_polyphase_filter_bank(bt, dtype, shape):
     pfb2 = bt.PolyphaseFilterBank(src, response, samples_per_frame=5)
     assert pfb2.samples_per_frame == 5
     assert_voltage(pfb2.read(), want[:pfb2.shape[0]].astype('c8'))
+
+
+def test_integrate_over_phase(bt):
+    """tests/test_integration.py:407-470: integrate in steps of pulse phase
+    (offsets found by inverting the phase callable, integration.py:188-228)."""
+    data, src = fake_pulsar(bt)
+    f0 = 1e4 / 125            # one cycle per 125 samples
+    t_ref = src.start_time
+
+    def phase(t):
+        return f0 * np.asarray(t - t_ref, dtype=float)
+
+    n_phase = 5
+    it = bt.Integrate(src, 1. / n_phase, phase, average=False)
+    assert it.shape == (128 * n_phase, 2)
+    out = it.read()
+    # Every phase bin gets 25 samples; the pulse is in the first.
+    np.testing.assert_array_equal(out['count'], 25)
+    want = data.reshape(-1, 25, 2).sum(1)
+    np.testing.assert_allclose(out['data'], want, rtol=1e-6)
+    it.seek(7)
+    assert abs((it.time - src.start_time) - 7 * 25 / 1e4) < 1e-9
+    np.testing.assert_allclose(it.read(3)['data'], want[7:10], rtol=1e-6)
