@@ -32,7 +32,7 @@ __all__ = ['Base', 'BaseTaskBase', 'TaskBase', 'PaddedTaskBase',
 META_ATTRIBUTES = {'frequency', 'sideband', 'polarization'}
 
 # Target size of the blocks of frames device tasks process per launch.
-BLOCK_BYTES = 1 << 30
+BLOCK_BYTES = 1 << 31
 
 
 def check_broadcast_to(value, sample_shape):

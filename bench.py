@@ -41,17 +41,17 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # rate/Hz, channel frequencies/Hz, DM, log2 N, frames per step
     'C2': dict(rate=8e6, freq=(1372e6 + 8e6 * np.arange(8)).reshape(8, 1),
-               sample_shape=(8, 2), dm=100., log2n=20, frames=8,
+               sample_shape=(8, 2), dm=100., log2n=20, frames=16,
                n_chan=1024, step=1e-3, seed=1234567 + 2,
                desc='8ch x 2pol x 8 MHz c64 -> Dedisperse(DM=100, N=2^20) -> '
                     'Channelize(1024) -> Power -> Integrate(1 ms)'),
     'C4': dict(rate=512e6, freq=8192e6, sample_shape=(2,), dm=1000.,
-               log2n=24, frames=4, n_chan=1024, step=1e-3, seed=1234567 + 4,
+               log2n=24, frames=8, n_chan=1024, step=1e-3, seed=1234567 + 4,
                desc='2pol x 512 MHz c64 -> Dedisperse(DM=1000, N=2^24) -> '
                     'Channelize(1024) -> Power -> Integrate(1 ms)'),
     # configs[4]: fold with a polynomial phase; profiles reduced over ranks.
     'C5': dict(rate=512e6, freq=8192e6, sample_shape=(2,), dm=1000.,
-               log2n=24, frames=4, n_chan=None, step=None, seed=1234567 + 5,
+               log2n=24, frames=8, n_chan=None, step=None, seed=1234567 + 5,
                fold=dict(n_phase=512, coef=[0.25, 29.946923,
                                             -3.77535e-10 / 2.]),
                desc='2pol x 512 MHz c64 -> Dedisperse(DM=1000, N=2^24) -> '
