@@ -1,8 +1,6 @@
-set -x
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+# ncu captures of bench.py (each only after the same command exited 0 without ncu)
 python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
 python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'dd_|chanpow' -s 12 -c 4 -o gpurun_out/r1_c2_full python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log
-ls -la gpurun_out | tail -8
+tail -2 gpurun_out/ncu_full.log
