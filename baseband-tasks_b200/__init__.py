@@ -14,11 +14,15 @@ from .base import (Base, BaseTaskBase, TaskBase, PaddedTaskBase, Task,  # noqa
 from ._units import Time  # noqa: F401
 from .fourier import fft_maker, CudaFFTMaker  # noqa: F401
 from .dm import DispersionMeasure  # noqa: F401
-from .dispersion import Disperse, Dedisperse  # noqa: F401
+from .dispersion import (Disperse, Dedisperse, DisperseSamples,  # noqa: F401
+                         DedisperseSamples)
+from .sampling import ShiftSamples  # noqa: F401
+from .convolution import Convolve  # noqa: F401
 from .channelize import Channelize, Dechannelize  # noqa: F401
 from .pfb import (sinc_hamming, PolyphaseFilterBankSamples,  # noqa: F401
                   PolyphaseFilterBank)
 from .functions import Square, Power  # noqa: F401
-from .integration import Integrate, Fold, PolynomialPhase  # noqa: F401
+from .integration import (Integrate, Fold, PulseStack,  # noqa: F401
+                          PolynomialPhase)
 from .generators import (StreamGenerator, EmptyStreamGenerator, Noise,  # noqa
                          NoiseGenerator, ArrayStream)

@@ -41,6 +41,8 @@ def as_device(x, dtype=None):
     t = torch()
     if not is_tensor(x):
         x = np.ascontiguousarray(x, dtype=dtype)
+        if not x.flags.writeable:
+            x = x.copy()
         x = t.from_numpy(x)
     elif dtype is not None and x.dtype != torch_dtype(dtype):
         x = x.to(torch_dtype(dtype))

@@ -60,6 +60,9 @@ _SIGNATURES = {
                               c_int, c_void_p, c_void_p, c_void_p]),
     'bbt_pfb_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                              c_int64, c_int64, c_int, c_void_p]),
+    'bbt_shift_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                               c_int, c_void_p]),
+    'bbt_convert_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'bbt_average_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int64, c_void_p]),
     'bbt_launch_count': (c_int64, []),

@@ -274,6 +274,41 @@ int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
   return rc;
 }
 
+int bbt_shift_exec(const void* in, void* out, const int64_t* offset,
+                   int64_t n_out, int64_t n_series, int item_bytes,
+                   void* stream) {
+  if (!in || !out || !offset) return fail(BBT_EINVAL, "null argument");
+  if (item_bytes != 4 && item_bytes != 8)
+    return fail(BBT_EUNSUPPORTED, "items must be 4 or 8 bytes");
+  if (n_out <= 0 || n_series <= 0) return BBT_OK;
+  const unsigned grid = grid_for(n_out * n_series, 256);
+  const long long* off = reinterpret_cast<const long long*>(offset);
+  if (item_bytes == 4)
+    BBT_LAUNCH(shift_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream),
+               static_cast<const float*>(in), static_cast<float*>(out), off,
+               (long long)n_out, (long long)n_series);
+  else
+    BBT_LAUNCH(shift_kernel<cf>, dim3(grid), dim3(256), 0, as_stream(stream),
+               static_cast<const cf*>(in), static_cast<cf*>(out), off,
+               (long long)n_out, (long long)n_series);
+  return check_launch("shift kernel");
+}
+
+int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
+                     void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (n <= 0) return BBT_OK;
+  if (to_real)
+    BBT_LAUNCH(complex_to_real_kernel, dim3(grid_for(n, 256)), dim3(256), 0,
+               as_stream(stream), static_cast<const cf*>(in),
+               static_cast<float*>(out), (long long)n);
+  else
+    BBT_LAUNCH(real_to_complex_kernel, dim3(grid_for(n, 256)), dim3(256), 0,
+               as_stream(stream), static_cast<const float*>(in),
+               static_cast<cf*>(out), (long long)n);
+  return check_launch("conversion kernel");
+}
+
 int bbt_average_exec(const void* sum, const void* count, void* out,
                      int64_t n_bins, int64_t inner, void* stream) {
   if (!sum || !count || !out) return fail(BBT_EINVAL, "null argument");

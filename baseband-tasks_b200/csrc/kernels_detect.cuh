@@ -449,6 +449,35 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
   }
 }
 
+// Integer sample shifts per series (sampling.py:380-425):
+// out[i][s] = in[i + offset[s]][s] for items of 4 or 8 bytes.
+template <typename T>
+BBT_GLOBAL void shift_kernel(const T* BBT_RESTRICT in, T* BBT_RESTRICT out,
+                             const long long* BBT_RESTRICT offset,
+                             long long n_out, long long S) {
+  const long long total = n_out * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i % S;
+    out[i] = in[i + offset[s] * S];
+  }
+}
+
+// Real samples to complex (zero imaginary part) and back (real part): lets
+// real-valued streams use the complex dedispersion kernels.
+BBT_GLOBAL void real_to_complex_kernel(const float* BBT_RESTRICT in,
+                                       cf* BBT_RESTRICT out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = mk(in[i], 0.f);
+}
+BBT_GLOBAL void complex_to_real_kernel(const cf* BBT_RESTRICT in,
+                                       float* BBT_RESTRICT out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i].x;
+}
+
 // out[b][c] = sum[b][c] / count[b]; 0/0 gives NaN like numpy's division.
 BBT_GLOBAL void average_kernel(const float* BBT_RESTRICT sum,
                                const unsigned long long* BBT_RESTRICT count,

@@ -17,12 +17,13 @@ import numpy as np
 from . import _buffers as B
 from . import _cabi
 from ._units import to_float, to_mhz
-from .base import PaddedTaskBase, getattr_if_none
+from .base import PaddedTaskBase, SetAttribute, getattr_if_none
 from .dm import DispersionMeasure
 from .fourier import fft_maker
 from .fourier.cuda import CudaFFTMaker
+from .sampling import ShiftSamples
 
-__all__ = ['Disperse', 'Dedisperse']
+__all__ = ['Disperse', 'Dedisperse', 'DisperseSamples', 'DedisperseSamples']
 
 
 class Disperse(PaddedTaskBase):
@@ -102,10 +103,9 @@ class Disperse(PaddedTaskBase):
                          next_fast_len=FFT.next_fast_len,
                          frequency=frequency, sideband=sideband,
                          start_time=start_time)
-        if not self.ih.complex_data:
-            raise NotImplementedError(
-                "coherent dedispersion of real-valued streams is not "
-                "implemented on the GPU; convert to complex first.")
+        # Real-valued streams (rfft/irfft in the reference) run through the
+        # complex kernels with a Hermitian response.
+        self._real = not self.ih.complex_data
         self._FFT = FFT
         self._dm = dm
         self.reference_frequency = reference_frequency
@@ -135,19 +135,55 @@ class Disperse(PaddedTaskBase):
             lib = _cabi.lib()
             f, r, s = self._chirp_par
             plan = ctypes.c_void_p()
+            dbl = ctypes.POINTER(ctypes.c_double)
             lib.check(lib.bbt_dedisperse_plan_create(
                 ctypes.byref(plan), self._ih_samples_per_frame,
                 self._n_series, self._pad_start, self.samples_per_frame,
                 len(f),
                 self._series_map.ctypes.data_as(
                     ctypes.POINTER(ctypes.c_int32)),
-                f.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                r.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                s.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                None if self._real else f.ctypes.data_as(dbl),
+                None if self._real else r.ctypes.data_as(dbl),
+                None if self._real else s.ctypes.data_as(
+                    ctypes.POINTER(ctypes.c_int8)),
                 float(self._dm), float(self._rate_mhz),
                 float(self._sample_offset), 0))
+            if self._real:
+                response = self._hermitian_response()
+                lib.check(lib.bbt_dedisperse_plan_set_response(
+                    plan, response.ctypes.data_as(ctypes.c_void_p)))
             self._plan = plan
         return self._plan
+
+    def _real_phase_factor(self):
+        """Phase factors at the rfft frequencies of each distinct chirp,
+        float64 phases rounded to complex64 (dispersion.py:115-129)."""
+        n = self._ih_samples_per_frame
+        fftfreq = np.fft.rfftfreq(n) * self._rate_mhz
+        f, r, s = self._chirp_par
+        d = DispersionMeasure.dispersion_delay_constant * float(self._dm)
+        out = np.empty((len(f), n // 2 + 1), np.complex64)
+        for c in range(len(f)):
+            freq = f[c] + fftfreq * s[c]
+            phase = d * freq * (1. / r[c] - 1. / freq)**2 * 1e6 * s[c]
+            if self._sample_offset != 0:
+                phase = phase + (self._sample_offset / self._rate_mhz
+                                 * fftfreq)
+            out[c] = np.exp(phase * (2j * np.pi))
+        return out
+
+    def _hermitian_response(self):
+        """Full-length response reproducing rfft -> x phase factor -> irfft:
+        Hermitian extension, with the imaginary parts that irfft ignores
+        (bins 0 and N/2) dropped."""
+        half = self._real_phase_factor()
+        n = self._ih_samples_per_frame
+        full = np.empty((half.shape[0], n), np.complex64)
+        full[:, :n // 2 + 1] = half
+        full[:, n // 2 + 1:] = half[:, n // 2 - 1:0:-1].conj()
+        full[:, 0] = half[:, 0].real
+        full[:, n // 2] = half[:, n // 2].real
+        return np.ascontiguousarray(full)
 
     @property
     def _fft(self):
@@ -167,6 +203,9 @@ class Disperse(PaddedTaskBase):
         shape ``(N,) + sample_shape``."""
         lib = _cabi.lib()
         n = self._ih_samples_per_frame
+        if self._real:
+            return self._real_phase_factor()[self._series_map].T.reshape(
+                (n // 2 + 1,) + self.ih.sample_shape)
         host = np.empty((len(self._chirp_par[0]), n), np.complex64)
         lib.check(lib.bbt_dedisperse_plan_get_response(
             self._get_plan(), host.ctypes.data_as(ctypes.c_void_p)))
@@ -188,7 +227,17 @@ class Disperse(PaddedTaskBase):
         lib = _cabi.lib()
         plan = self._get_plan()
         host = not B.is_tensor(data)
-        x = B.as_device(data, dtype=np.complex64)
+        if self._real:
+            return self._task_frames_real(data, n_frames, out, host)
+        result = self._exec_frames(B.as_device(data, dtype=np.complex64),
+                                   n_frames, out)
+        if out is None and host:
+            return B.as_host(result)
+        return result
+
+    def _exec_frames(self, x, n_frames, out):
+        lib = _cabi.lib()
+        plan = self._get_plan()
         S, spf = self._n_series, self.samples_per_frame
         N = self._ih_samples_per_frame
         assert x.shape[0] == (n_frames - 1) * spf + N
@@ -204,9 +253,27 @@ class Disperse(PaddedTaskBase):
         lib.check(lib.bbt_dedisperse_exec(
             plan, B.ptr(x), spf * S, n_frames, 0, B.ptr(result), spf * S,
             B.ptr(self._work), _cabi.stream_ptr()))
-        if out is None and host:
-            return B.as_host(result)
         return result
+
+    def _task_frames_real(self, data, n_frames, out, host):
+        lib = _cabi.lib()
+        x = B.as_device(data, dtype=np.float32)
+        xc = B.empty(x.shape, np.complex64)
+        lib.check(lib.bbt_convert_exec(B.ptr(x), B.ptr(xc), x.numel(), 0,
+                                       _cabi.stream_ptr()))
+        yc = self._exec_frames(xc, n_frames, None)
+        result = out
+        if result is None or result.dtype != B.torch_dtype(np.float32):
+            result = B.empty(yc.shape, np.float32)
+        lib.check(lib.bbt_convert_exec(B.ptr(yc), B.ptr(result), yc.numel(),
+                                       1, _cabi.stream_ptr()))
+        if out is not None:
+            if result is not out:
+                out.copy_(result)
+            return out
+        if self.dtype != np.dtype(np.float32):
+            result = result.to(B.torch_dtype(self.dtype))
+        return B.as_host(result) if host else result
 
     def task(self, data, out=None):
         """One frame: N input samples to ``samples_per_frame`` outputs."""
@@ -234,6 +301,56 @@ class Dedisperse(Disperse):
     Parameters are as for `Disperse`; the dispersion measure is removed
     rather than added.
     """
+
+    def __init__(self, ih, dm, *, reference_frequency=None,
+                 samples_per_frame=None, frequency=None, sideband=None):
+        super().__init__(ih, -DispersionMeasure(dm),
+                         reference_frequency=reference_frequency,
+                         samples_per_frame=samples_per_frame,
+                         frequency=frequency, sideband=sideband)
+
+    @property
+    def dm(self):
+        return -self._dm
+
+
+class DisperseSamples(ShiftSamples):
+    """Incoherently shift a time stream to give it a dispersive time delay
+    (dispersion.py:193-251): only whole-sample shifts by the delay at the
+    mid-channel frequency, no in-channel smearing.
+
+    Parameters are as for `Disperse`.
+    """
+
+    def __init__(self, ih, dm, *, reference_frequency=None,
+                 samples_per_frame=None, frequency=None, sideband=None):
+        if frequency is not None or sideband is not None:
+            ih = SetAttribute(ih, frequency=frequency, sideband=sideband)
+        frequency = ih.frequency
+        freq_mhz = to_mhz(frequency)
+        if not ih.complex_data:
+            # Mid-channel frequency for real data.
+            freq_mhz = freq_mhz + ih.sideband * to_mhz(ih.sample_rate) / 2.
+        if reference_frequency is None:
+            fref_mhz = np.mean(freq_mhz)
+            reference_frequency = fref_mhz * 1e6 * _unit_of(frequency)
+        else:
+            fref_mhz = to_mhz(reference_frequency)
+        dm = DispersionMeasure(dm)
+        time_delay = _time_delay(dm, freq_mhz, fref_mhz)
+        shift = time_delay * (to_mhz(ih.sample_rate) * 1e6)
+        super().__init__(ih, shift, samples_per_frame=samples_per_frame)
+        self.reference_frequency = reference_frequency
+        self._dm = dm
+
+    @property
+    def dm(self):
+        return self._dm
+
+
+class DedisperseSamples(DisperseSamples):
+    """Incoherently shift a time stream to correct for a dispersive time
+    delay (dispersion.py:254-298)."""
 
     def __init__(self, ih, dm, *, reference_frequency=None,
                  samples_per_frame=None, frequency=None, sideband=None):

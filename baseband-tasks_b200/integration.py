@@ -26,7 +26,7 @@ from .base import BaseTaskBase
 from .channelize import Channelize
 from .functions import Power
 
-__all__ = ['Integrate', 'Fold', 'PolynomialPhase']
+__all__ = ['Integrate', 'Fold', 'PulseStack', 'PolynomialPhase']
 
 _MAX_BINS_PER_LAUNCH = 32768
 # Fewest output values for which averages are formed inside the kernels.
@@ -517,3 +517,38 @@ def _cycles(phases):
     if hasattr(phases, 'to_value'):
         return phases.to_value('cycle')
     return phases
+
+
+class PulseStack(BaseTaskBase):
+    """Create a stream of pulse profiles (integration.py:398-477).
+
+    Integrates in ``n_phase`` phase bins per pulse period (an `Integrate` in
+    steps of ``1 / n_phase`` cycles of the ``phase`` callable, which has to
+    include the cycle count) and presents the result as one profile per pulse.
+
+    Parameters are as for `Fold`, without ``step``.
+    """
+
+    def __init__(self, ih, n_phase, phase, *,
+                 start=0, average=True, samples_per_frame=1, dtype=None):
+        phased = Integrate(ih, 1. / n_phase, phase, start=start,
+                           average=average,
+                           samples_per_frame=samples_per_frame * n_phase,
+                           dtype=dtype)
+        shape = (phased.shape[0] // n_phase, n_phase) + phased.shape[1:]
+        super().__init__(phased, shape=shape,
+                         sample_rate=phased.sample_rate / n_phase,
+                         samples_per_frame=samples_per_frame,
+                         dtype=dtype)
+        self.n_phase = n_phase
+
+    def _read_frame(self, frame_index):
+        # Read the frame of the phase-binned stream directly.
+        out = self.ih._read_frame(frame_index)
+        if len(out) != self.ih.samples_per_frame:
+            # Remove a possible incomplete cycle in the last frame.
+            out = out[:(len(out) // self.n_phase) * self.n_phase]
+        return out.reshape((-1,) + self.sample_shape)
+
+    def _tell_time(self, offset):
+        return self.ih._tell_time(offset * self.n_phase)

@@ -152,6 +152,22 @@ int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
                  int64_t n_tap, int64_t inner, int64_t n_spec, int is_real,
                  void* stream);
 
+/* ---- Integer sample shifts: replaces ShiftSamples.task (sampling.py:380-425,
+ * used by DisperseSamples/DedisperseSamples, dispersion.py:193-298):
+ * out[i][s] = in[i + offset[s]][s] for i < n_out, with offset (device int64,
+ * one per series, >= 0) and items of item_bytes = 4 (float32) or 8 (complex64). */
+int bbt_shift_exec(const void* in, void* out, const int64_t* offset,
+                   int64_t n_out, int64_t n_series, int item_bytes,
+                   void* stream);
+
+/* ---- Conversion between real float32 and complex64 samples (n values):
+ * to_real == 0 sets the imaginary part to zero, to_real != 0 keeps the real
+ * part.  Lets real-valued streams (rfft/irfft in the reference,
+ * fourier/numpy.py:41-49) go through the complex dedispersion kernels with a
+ * Hermitian response. */
+int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
+                     void* stream);
+
 /* ---- Averaging: out[b][c] = sum[b][c] / count[b] (NaN for empty bins),
  * the division Integrate._read_frame does (integration.py:268-269). */
 int bbt_average_exec(const void* sum, const void* count, void* out,

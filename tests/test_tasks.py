@@ -10,7 +10,7 @@ import pytest
 
 import bbt_oracle as orc
 
-from test_kernels import assert_voltage, assert_power, cnoise
+from test_kernels import assert_voltage, assert_power, cnoise, rms
 
 
 @pytest.fixture
@@ -615,3 +615,135 @@ def test_integrate_over_phase(bt):
     it.seek(7)
     assert abs((it.time - src.start_time) - 7 * 25 / 1e4) < 1e-9
     np.testing.assert_allclose(it.read(3)['data'], want[7:10], rtol=1e-6)
+
+
+# ------------------------------------------------- real streams, convolution
+def test_disperse_real_stream(bt):
+    """tests/test_dispersion.py:206-240: a real-valued two-sideband stream
+    (rfft / irfft in the reference)."""
+    n = 30000
+    rng = np.random.default_rng(31)
+    x = rng.normal(size=(n, 2)).astype('f4')
+    rate = 256e3
+    freq = np.array([299.936e6, 300.064e6])
+    sideband = np.array([1, -1])
+    dm = 1000. * 0.05 / 0.039342251 * 0.01
+    src = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=1000,
+                         frequency=freq, sideband=sideband)
+    disp = bt.Disperse(src, dm)
+    op = orc.DispersePlan(dm, freq / 1e6, sideband, rate / 1e6, False, n,
+                          1000, (2,), fast_len=orc.next_pow2)
+    assert (disp._pad_start, disp._pad_end, disp._ih_samples_per_frame) == (
+        op.pad_start, op.pad_end, op.N)
+    assert disp.dtype == np.float32 and disp.shape == (op.n_out, 2)
+    want = orc.disperse(x, op)
+    got = disp.read()
+    assert got.dtype == np.float32
+    assert_voltage(got, want)
+    pf = disp.phase_factor
+    assert pf.shape == (op.N // 2 + 1, 2)
+    assert np.max(np.abs(pf - op.phase_factor('f4'))) < 2e-6
+    # and back again
+    dedisp = bt.Dedisperse(disp, dm)
+    back = dedisp.read()
+    off = int(round((dedisp.start_time - src.start_time) * rate))
+    # Overlap-save truncates the chirp's response at the padding, so the
+    # round trip of a noise stream is close, not exact (the reference's own
+    # round-trip test uses atol=1e-2 on a unit pulse).
+    assert rms(back - x[off:off + back.shape[0]]) < 0.1 * rms(x)
+
+
+@pytest.mark.parametrize('dtype', ['c8', 'f4'])
+def test_convolve(bt, dtype):
+    """tests/test_convolution.py:14-39 on a synthetic stream."""
+    from test_kernels import rms as _rms  # noqa: F401
+    rng = np.random.default_rng(41)
+    x = rng.normal(size=(16000, 2))
+    if dtype == 'c8':
+        x = x + 1j * rng.normal(size=x.shape)
+    x = x.astype(dtype)
+    src = bt.ArrayStream(x, start_time(bt), 1e4, samples_per_frame=1000)
+    ct = bt.Convolve(src, np.ones(3), samples_per_frame=1024 - 2)
+    expected = x[:-2] + x[1:-1] + x[2:]
+    data1 = ct.read()
+    assert ct.tell() == ct.shape[0] == x.shape[0] - 2
+    assert abs((ct.start_time - src.start_time) - 2 / 1e4) < 1e-9
+    assert data1.dtype == np.dtype(dtype)
+    assert np.allclose(expected, data1, atol=1e-4)
+    ct.seek(-3, 2)
+    assert np.allclose(expected[-3:], ct.read(), atol=1e-4)
+    # Per-series responses and an offset.
+    response = rng.normal(size=(5, 2))
+    ct2 = bt.Convolve(src, response, offset=2)
+    want = np.stack([np.convolve(x[:, i], response[:, i], mode='valid')
+                     for i in range(2)], axis=1)
+    assert abs((ct2.start_time - src.start_time) - 2 / 1e4) < 1e-9
+    got = ct2.read()
+    assert got.shape == want.shape
+    assert np.allclose(got, want, atol=2e-4)
+
+
+def test_disperse_samples(bt):
+    """tests/test_dispersion.py:309-358: integer shifts of a giant pulse in a
+    real two-sideband stream land exactly where the delays say, and
+    DedisperseSamples undoes DisperseSamples exactly."""
+    rate, n, gp_sample = 256e3, 328000, 128000
+    x = np.zeros((n, 2), 'f4')
+    x[gp_sample] = 1.
+    freq = np.array([299.936e6, 300.064e6])
+    sideband = np.array([1, -1])
+    dm = 1000. * 0.05 / 0.039342251
+    src = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=1000,
+                         frequency=freq, sideband=sideband)
+    for fref in (None, 300e6, 300.064e6, 200e6):
+        disperse = bt.DisperseSamples(src, dm, reference_frequency=fref)
+        center = (disperse.frequency
+                  + disperse.sideband * disperse.sample_rate / 2.)
+        delay = bt.DispersionMeasure(dm).time_delay(
+            center, disperse.reference_frequency)
+        t_gp = gp_sample / rate + delay         # seconds since stream start
+        disperse.seek(src.start_time + t_gp.min())
+        around = disperse.read(gp_sample)
+        diff = int(np.round((delay.max() - delay.min()) * rate))
+        expected = np.zeros_like(around)
+        expected[0, t_gp.argmin()] = 1.
+        expected[diff, t_gp.argmax()] = 1.
+        np.testing.assert_array_equal(around, expected)
+    disperse = bt.DisperseSamples(src, dm, reference_frequency=300e6)
+    dedisperse = bt.DedisperseSamples(disperse, dm, reference_frequency=300e6)
+    assert dedisperse.dm == dm and dedisperse._dm == -dm
+    dedisperse.seek(src.start_time + gp_sample / rate)
+    dedisperse.seek(-1024, 1)
+    gp_dd = dedisperse.read(2048)
+    np.testing.assert_array_equal(gp_dd, x[gp_sample - 1024:gp_sample + 1024])
+    # complex samples, arbitrary shifts
+    z = cnoise(np.random.default_rng(9), (5000, 3))
+    zs = bt.ArrayStream(z, start_time(bt), 1e3, samples_per_frame=700)
+    sh = bt.ShiftSamples(zs, np.array([3, -2, 0]), samples_per_frame=512)
+    assert sh.shape == (4995, 3)
+    assert abs((sh.start_time - zs.start_time) - 3 / 1e3) < 1e-12
+    out = sh.read()
+    for i, s in enumerate([3, -2, 0]):
+        np.testing.assert_array_equal(out[:, i], z[3 - s:3 - s + 4995, i])
+
+
+def test_pulse_stack(bt):
+    """tests/test_integration.py:430-470: one profile per pulse."""
+    data, src = fake_pulsar(bt)
+    f0 = 1e4 / 125
+    t_ref = src.start_time
+
+    def phase(t):
+        return f0 * np.asarray(t - t_ref, dtype=float)
+
+    ps = bt.PulseStack(src, 5, phase, average=False)
+    assert ps.shape == (128, 5, 2)
+    assert abs(float(ps.sample_rate) - 1.) < 1e-12      # per cycle
+    out = ps.read()
+    np.testing.assert_array_equal(out['count'], 25)
+    want = data.reshape(128, 5, 25, 2).sum(2)
+    np.testing.assert_allclose(out['data'], want, rtol=1e-6)
+    avg = bt.PulseStack(src, 5, phase, samples_per_frame=4)
+    avg.seek(100)
+    np.testing.assert_allclose(avg.read(8), want[100:108] / 25, rtol=1e-6)
+    assert abs((avg.time - src.start_time) - 108 * 125 / 1e4) < 1e-9
