@@ -1,6 +1,4 @@
 // C-ABI implementation (see include/bbt_b200.h): coherent (de)dispersion.
-#include <type_traits>
-
 #include "common.cuh"
 #include "kernels_dedisperse.cuh"
 
@@ -10,10 +8,7 @@ struct bbt_dedisperse_plan {
   int64_t n, n_series, pad_start, n_valid, n_chirp;
   int log2n, log2n1, log2n2;
   int planar;      // work-buffer layout of the three-pass split
-  int col_e32;     // 32 elements per thread in short column FFTs
-  int row16;       // 16 elements per thread in the row FFTs
   int half;        // 256-thread CTAs, half-size tiles
-  int col16;       // 16 values per thread, 1024 threads, in column passes
   const cf* tw1;   // roots of unity for the column FFTs (n1)
   const cf* tw2;   // for the row FFTs (n2), or the whole single-pass frame
   cf* big_lo;
@@ -28,27 +23,22 @@ constexpr int kColThreads = 512;
 
 // Elements per thread of the column FFTs.  HALF: 256-thread CTAs with half
 // the lanes (64 KB tiles, two CTAs per SM).
-template <int L1, bool E32, bool HALF>
+template <int L1, bool HALF>
 struct ColCfg {
-  static constexpr int LOG2E = L1 <= 4 ? L1 : ((L1 <= 8 && !E32) ? 4 : 5);
+  static constexpr int LOG2E = L1 <= 4 ? L1 : (L1 <= 8 ? 4 : 5);
   using type = FftCfg<L1, LOG2E, HALF ? kColThreads / 2 : kColThreads>;
 };
-// Experimental: 16 values per thread in 1024-thread CTAs (same tile).
-template <int L1>
-struct ColCfg16 {
-  using type = FftCfg<L1, (L1 < 4 ? L1 : 4), 1024>;
-};
 
-int col_lanes(int l1, bool e32) {
-  const int log2e = l1 <= 4 ? l1 : ((l1 <= 8 && !e32) ? 4 : 5);
+
+int col_lanes(int l1) {
+  const int log2e = l1 <= 4 ? l1 : (l1 <= 8 ? 4 : 5);
   return kColThreads >> (l1 - log2e);
 }
 
-template <int L1, bool E32, bool HALF = false, bool C16 = false>
+template <int L1, bool HALF = false>
 int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
                   bbt_stream_t st) {
-  using C = typename std::conditional<C16, typename ColCfg16<L1>::type,
-                                      typename ColCfg<L1, E32, HALF>::type>::type;
+  using C = typename ColCfg<L1, HALF>::type;
   DdArgs a = a0;
   if (HALF) a.ahead *= 2;
   const int64_t cols = (a.N >> L1) * a.S;
@@ -62,12 +52,10 @@ int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
   return check_launch("dedispersion column kernel");
 }
 
-// ROW16: 16 elements per thread in 1024-thread CTAs instead of 32 in 512 (or
-// 256 for planar rows below 2^14 points, two CTAs per SM).
-template <int L2, bool PLANAR, bool ROW16, bool HALF = false>
+// HALF: 256-thread CTAs on half-size tiles, two per SM.
+template <int L2, bool PLANAR, bool HALF = false>
 int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
-  using C = FftCfg<L2, ROW16 ? 4 : 5,
-                   ROW16 ? 1024 : (HALF ? 256 : 512)>;
+  using C = FftCfg<L2, 5, HALF ? 256 : 512>;
   DdArgs a = a0;
   if (HALF) a.ahead *= 2;
   const int64_t n1 = a.N >> L2;
@@ -155,10 +143,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->big_lo = p->big_hi = p->chirp = nullptr;
   p->series_map = nullptr;
   p->planar = 1;
-  p->col_e32 = (hint >> 10) & 1;
-  p->row16 = (hint >> 11) & 1;
   p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
-  p->col16 = (hint >> 15) & 1;
   const int hint_l1 = hint & 0xff;
   const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;
   if (l <= kLog2TwiddleTable && (n_series == 1 || l <= 10) && !hint_l1) {
@@ -171,7 +156,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     int l1 = l - l2;
     bool planar = true;
     if (n_series > 1 && !force_planar) {
-      const int tn = col_lanes(l1, p->col_e32) / (int)std::min<int64_t>(
+      const int tn = col_lanes(l1) / (int)std::min<int64_t>(
                                                      n_series, 1 << 20);
       // Rows of >= 8 interleaved series move in 64-byte runs as they are.
       if (((tn < 8 || n_series >= 8) && l - 10 <= 12) || force_inter) {
@@ -355,38 +340,26 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
     return rc;
   }
   if (!work) return fail(BBT_EINVAL, "dedispersion needs a work buffer");
-  const bool e32 = p->col_e32;
   const bool hcol = p->half & 1, hrow = p->half & 2;
-  const bool c16 = p->col16 && p->log2n1 >= 9;
-#define F(L)                                                              \
-  rc = c16 ? launch_dd_col<L, false, false, true>(false, a, n_frames, st) \
-       : hcol ? launch_dd_col<L, false, true>(false, a, n_frames, st)     \
-            : (e32 ? launch_dd_col<L, true>(false, a, n_frames, st)       \
-                   : launch_dd_col<L, false>(false, a, n_frames, st))
+#define F(L)                                                        \
+  rc = hcol ? launch_dd_col<L, true>(false, a, n_frames, st)        \
+            : launch_dd_col<L, false>(false, a, n_frames, st)
   BBT_FOR_LOG2(p->log2n1, F)
 #undef F
   if (rc) return rc;
   rc = BBT_EUNSUPPORTED;
-#define F(L)                                                                  \
-  rc = hrow ? (p->planar                                                      \
-                   ? launch_dd_row<L, true, false, true>(a, n_frames, st)     \
-                   : launch_dd_row<L, false, false, true>(a, n_frames, st))   \
-            : (p->planar                                                      \
-                   ? (p->row16                                                \
-                          ? launch_dd_row<L, true, true>(a, n_frames, st)     \
-                          : launch_dd_row<L, true, false>(a, n_frames, st))   \
-                   : (p->row16                                                \
-                          ? launch_dd_row<L, false, true>(a, n_frames, st)    \
-                          : launch_dd_row<L, false, false>(a, n_frames, st)))
+#define F(L)                                                             \
+  rc = hrow ? (p->planar ? launch_dd_row<L, true, true>(a, n_frames, st)  \
+                         : launch_dd_row<L, false, true>(a, n_frames, st)) \
+            : (p->planar ? launch_dd_row<L, true>(a, n_frames, st)        \
+                         : launch_dd_row<L, false>(a, n_frames, st))
   BBT_FOR_ROW(p->log2n2, F)
 #undef F
   if (rc) return rc;
   rc = BBT_EUNSUPPORTED;
-#define F(L)                                                              \
-  rc = c16 ? launch_dd_col<L, false, false, true>(true, a, n_frames, st)  \
-       : hcol ? launch_dd_col<L, false, true>(true, a, n_frames, st)      \
-            : (e32 ? launch_dd_col<L, true>(true, a, n_frames, st)        \
-                   : launch_dd_col<L, false>(true, a, n_frames, st))
+#define F(L)                                                        \
+  rc = hcol ? launch_dd_col<L, true>(true, a, n_frames, st)         \
+            : launch_dd_col<L, false>(true, a, n_frames, st)
   BBT_FOR_LOG2(p->log2n1, F)
 #undef F
   return rc;

@@ -4,16 +4,7 @@
 
 using namespace bbt;
 
-namespace {
-int g_chan_variant = 0;  // bbt_tune(1, v): tile shape of the 1024-channelizer
-}
-
 extern "C" {
-
-int bbt_tune(int key, int value) {
-  if (key == 1) g_chan_variant = value;
-  return BBT_OK;
-}
 
 // ----------------------------------------------------------------- detection
 int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
@@ -49,7 +40,7 @@ struct ChanCfg {
   using type = FftCfg<L, LOG2E, THREADS>;
 };
 
-template <class C, bool INTEGRATE, int MINB = 1>
+template <class C, bool INTEGRATE>
 int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st);
 
@@ -57,33 +48,20 @@ template <int L, bool INTEGRATE>
 int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                    bbt_stream_t st) {
   if constexpr (L == 10) {
-    if (g_chan_variant == 1)
-      return launch_chanpow_cfg<FftCfg<10, 3, 1024>, INTEGRATE>(a, n_bins,
-                                                                max_width, st);
-    if (g_chan_variant == 2)
-      return launch_chanpow_cfg<FftCfg<10, 4, 256>, INTEGRATE>(a, n_bins,
-                                                               max_width, st);
-    if (g_chan_variant == 3)
-      return launch_chanpow_cfg<FftCfg<10, 3, 512>, INTEGRATE>(a, n_bins,
-                                                               max_width, st);
-    if (g_chan_variant == 5)
+    // Measured best for the 1024-channel case: 32 values per thread; 16
+    // lanes when spectra are written out, 8 (with the accumulators in
+    // registers) when they are integrated.
+    if (!INTEGRATE)
       return launch_chanpow_cfg<FftCfg<10, 5, 512>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
-    if (g_chan_variant == 6)
-      return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE, 2>(
-          a, n_bins, max_width, st);
-    if (g_chan_variant == 0 && !INTEGRATE)
-      return launch_chanpow_cfg<FftCfg<10, 5, 512>, INTEGRATE>(a, n_bins,
-                                                               max_width, st);
-    if (g_chan_variant == 0 || g_chan_variant == 4)
-      return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
-                                                               max_width, st);
+    return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
+                                                             max_width, st);
   }
   return launch_chanpow_cfg<typename ChanCfg<L>::type, INTEGRATE>(
       a, n_bins, max_width, st);
 }
 
-template <class C, bool INTEGRATE, int MINB>
+template <class C, bool INTEGRATE>
 int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st) {
   constexpr int64_t units = C::G / 2;  // (sub-stream, m) pairs per CTA
@@ -97,7 +75,7 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
   const int64_t blocks = ceil_div(msub * a.M, units);
   dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
   const size_t smem = C::SMEM_BYTES;
-  auto kern = chanpow_kernel<C, INTEGRATE, MINB>;
+  auto kern = chanpow_kernel<C, INTEGRATE>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
   prof_next_name = INTEGRATE ? "chanpow_integrate" : "chanpow";

@@ -80,8 +80,8 @@ struct ChanPowArgs {
 // bytes per time sample.  After the transform the two threads holding X and Y
 // of a channel swap half of their values (one shuffle per value), and each
 // forms all four products for every other channel.
-template <class C, bool INTEGRATE, int MINB = 1>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, MINB) chanpow_kernel(ChanPowArgs a) {
+template <class C, bool INTEGRATE>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
   static_assert(C::G % 2 == 0 && C::E % 2 == 0, "pairs of lanes and values");
   cf* smem = BBT_SMEM(cf);
   const int tid = threadIdx.x;

@@ -45,7 +45,7 @@ const char* bbt_last_error(void);
 /* ---- FFT: replaces np.fft.{fft,ifft,rfft,irfft}(a, axis, norm) as called by
  * NumpyFFTBase (fourier/numpy.py:33-49) for the FFT objects FFTMakerBase.__call__
  * creates (fourier/base.py:262-311).  Data are [outer][n][inner]; the
- * transform runs along the middle axis.  n must be a power of two; n > 8192
+ * transform runs along the middle axis.  n must be a power of two; n > 16384
  * needs inner == 1 and a work buffer of bbt_fft_plan_work_bytes().
  * scale multiplies the output (1, 1/n or 1/sqrt(n): fourier/base.py:95-104). */
 int bbt_fft_plan_create(bbt_fft_plan** plan, int64_t n, int64_t outer,
@@ -64,8 +64,13 @@ int bbt_fft_plan_destroy(bbt_fft_plan* plan);
  *   F = freq + fftfreq sideband      (dm.py:103-105, dispersion.py:117-126)
  * with one (freq, f_ref, sideband) triple per distinct chirp; series_map[s]
  * (host, n_series ints) says which chirp series s uses.  dm is the dispersing
- * DM (Dedisperse passes -dm, dispersion.py:184).  log2n1_hint selects the
- * column-FFT length of the three-pass split (0 = automatic). */
+ * DM (Dedisperse passes -dm, dispersion.py:184).  With freq_mhz == NULL no
+ * chirp is generated (use bbt_dedisperse_plan_set_response).  hint = 0 lets
+ * the library choose the three-pass split and layout; otherwise bits 0-7:
+ * log2 of the column-FFT length, bit 8 / 9: force the planar / interleaved
+ * work-buffer layout, bits 12 / 13: half-size (two per SM) tiles in the
+ * column / row passes, bit 14: full-size row tiles for the interleaved
+ * layout (tuning and tests). */
 int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
                                int64_t n_series, int64_t pad_start,
                                int64_t n_valid, int64_t n_chirp,
@@ -73,7 +78,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
                                const double* freq_mhz, const double* fref_mhz,
                                const int8_t* sideband, double dm,
                                double rate_mhz, double sample_offset,
-                               int log2n1_hint);
+                               int hint);
 /* Replace the chirp by an arbitrary response (host, [n_chirp][n] complex64,
  * natural FFT bin order): Convolve-style reuse (convolution.py:97-119). */
 int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* plan,
@@ -179,8 +184,6 @@ int bbt_average_exec(const void* sum, const void* count, void* out,
  * bbt_profile_report: wait for them and write "kernel count total_ms" lines
  * (NUL-terminated) into buf, clearing the records. */
 int64_t bbt_launch_count(void);
-/* Development knob: select among compiled tile shapes (key 1: channelizer). */
-int bbt_tune(int key, int value);
 int bbt_profile_enable(int on);
 int bbt_profile_report(char* buf, int64_t size);
 

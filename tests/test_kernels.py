@@ -239,20 +239,19 @@ def test_dedisperse_small(backend, case):
         dd.close()
 
 
-INTER, E32, R16 = 512, 1024, 2048   # plan hints: layout, thread shapes
+INTER, PLANAR, HALF, FULLROW = 512, 256, 4096 | 8192, 16384   # plan hints
 
 
 @pytest.mark.parametrize('log2n,S,log2n1', [
     (14, 1, 0), (14, 2, 0), (15, 3, 5), (16, 2, 3), (14, 2, 4 | INTER),
-    (13, 16, INTER), (15, 3, 5 | INTER | E32), (15, 1, 5 | E32),
-    (15, 1, 5 | R16), (14, 2, 4 | INTER | R16), (24, 2, R16),
-    (15, 2, 5 | 4096 | 8192), (14, 16, 4 | INTER | 4096 | 8192),
-    (20, 2, 0), (20, 16, 0), (20, 16, INTER), (20, 16, 6 | E32),
-    (22, 2, 10), (24, 2, 0)])
+    (13, 16, INTER), (15, 3, 5 | INTER | FULLROW), (15, 5, 5 | PLANAR),
+    (15, 2, 5 | HALF), (14, 16, 4 | INTER | HALF), (14, 7, 3 | INTER),
+    (20, 2, 0), (20, 16, 0), (20, 16, INTER | FULLROW), (20, 16, 6 | PLANAR),
+    (22, 2, 10), (24, 2, 0), (21, 3, 0)])
 def test_dedisperse_large(backend, log2n, S, log2n1):
     if log2n > 16 and not backend.big:
         pytest.skip('too slow on host threads')
-    if backend.name == 'emu' and log2n > 14 and S > 2 and not (log2n1 & E32):
+    if backend.name == 'emu' and log2n > 14 and S > 3:
         pytest.skip('too slow on host threads')
     rng = np.random.default_rng(500 + log2n)
     N = 1 << log2n

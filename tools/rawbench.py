@@ -120,13 +120,13 @@ def dd_plan(N, S, pad_start, n_valid, log2n1):
 
 
 def sec_dd():
-    # planar, interleaved, E=32 column FFTs, 16-element row FFTs
-    P, I, E, R = 256, 512, 1024, 2048
+    P, I = 256, 512       # planar / interleaved work-buffer layout
     HC, HR = 4096, 8192   # half-size tiles in column / row passes
-    C16 = 32768           # 16 values per thread in column passes
+    FR = 16384            # full-size row tiles for the interleaved layout
     for (N, S, frames, hints) in (
-            (1 << 20, 16, 4, (I, I | C16)),
-            (1 << 24, 2, 2, (0, C16)),
+            (1 << 20, 16, 4, (0, I | FR, P, I | HC)),
+            (1 << 24, 2, 2, (0, HC, 11 | P | HR)),
+            (1 << 22, 2, 4, (0, HC, 9 | P | HR)),
             (1 << 14, 2050, 2, (0,)),
             (1 << 13, 2050, 4, (0,))):
         pad = N // 5
@@ -152,14 +152,6 @@ def sec_dd():
 
 
 def sec_chan():
-    for variant in (0, 5, 6):
-        lib.bbt_tune(1, variant)
-        print('channelizer tile variant', variant)
-        _sec_chan()
-    lib.bbt_tune(1, 0)
-
-
-def _sec_chan():
     n, m = 1024, 8
     n_spec = 1 << 13
     x = torch.randn(n_spec * n * m * 2, dtype=torch.complex64, device=dev)
