@@ -248,6 +248,7 @@ struct FftCfg {
 // stage are compile-time constants in padded positions (see fft_stage).
 template <int PADSHIFT>
 struct SmemLaneFast {
+  static constexpr bool kLaneFast = true;
   cf* base;
   int g, G;
   static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
@@ -256,6 +257,7 @@ struct SmemLaneFast {
 };
 template <int PADSHIFT>
 struct SmemLaneSlow {
+  static constexpr bool kLaneFast = false;
   cf* base;  // already offset to this lane
   static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
   BBT_HD cf& ref(int s) const { return base[s]; }
@@ -296,22 +298,21 @@ BBT_HD void prefetch_l2(const void* p) {
 #endif
 }
 
-// v[e] <- v[e] * base * step^e (MODE 0), or conj(v[e] * base * step^e) * scale
-// (MODE 1), for e < 2^BITS, with pw[b] = step^(2^b): a linear phase ramp at
-// one complex multiply per element and per power.
+// v[e] <- v[e] * base * step^e (MODE 0), or its conjugate (MODE 1), for
+// e < 2^BITS, with pw[b] = step^(2^b): a linear phase ramp at one complex
+// multiply per element and per power.  (A real scale goes into ``base``.)
 template <int BITS, int MODE>
 struct Ramp {
-  static BBT_HD void run(cf* v, cf w, const cf* pw, float scale) {
-    Ramp<BITS - 1, MODE>::run(v, w, pw, scale);
-    Ramp<BITS - 1, MODE>::run(v + (1 << (BITS - 1)), cmul(w, pw[BITS - 1]), pw,
-                              scale);
+  static BBT_HD void run(cf* v, cf w, const cf* pw) {
+    Ramp<BITS - 1, MODE>::run(v, w, pw);
+    Ramp<BITS - 1, MODE>::run(v + (1 << (BITS - 1)), cmul(w, pw[BITS - 1]), pw);
   }
 };
 template <int MODE>
 struct Ramp<0, MODE> {
-  static BBT_HD void run(cf* v, cf w, const cf*, float scale) {
+  static BBT_HD void run(cf* v, cf w, const cf*) {
     cf r = cmul(v[0], w);
-    v[0] = MODE ? mk(r.x * scale, -r.y * scale) : r;
+    v[0] = MODE ? mk(r.x, -r.y) : r;
   }
 };
 
@@ -324,6 +325,9 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 #endif
 }
 
+#ifndef BBT_TW_SQUARE
+#define BBT_TW_SQUARE 1  // powers of two by squaring instead of look-ups
+#endif
 // b[r] *= w^r for r < R, with w = tw[kk]: powers of two are looked up, the
 // others are products of two looked-up or derived values.
 template <int R>
@@ -332,11 +336,11 @@ BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
     cf w[8];  // w^1 .. w^7
     w[1] = ldtw(tw, kk);
     if constexpr (R >= 4) {
-      w[2] = ldtw(tw, 2 * kk);
+      w[2] = BBT_TW_SQUARE ? cmul(w[1], w[1]) : ldtw(tw, 2 * kk);
       w[3] = cmul(w[2], w[1]);
     }
     if constexpr (R >= 8) {
-      w[4] = ldtw(tw, 4 * kk);
+      w[4] = BBT_TW_SQUARE ? cmul(w[2], w[2]) : ldtw(tw, 4 * kk);
       w[5] = cmul(w[4], w[1]);
       w[6] = cmul(w[4], w[2]);
       w[7] = cmul(w[4], w[3]);
@@ -345,12 +349,12 @@ BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
 #pragma unroll
     for (int r = 1; r < LOW; ++r) b[r] = cmul(b[r], w[r]);
     if constexpr (R >= 16) {
-      cf hi = ldtw(tw, 8 * kk);
+      cf hi = BBT_TW_SQUARE ? cmul(w[4], w[4]) : ldtw(tw, 8 * kk);
       b[8] = cmul(b[8], hi);
 #pragma unroll
       for (int r = 1; r < 8; ++r) b[8 + r] = cmul(b[8 + r], cmul(hi, w[r]));
       if constexpr (R >= 32) {
-        cf hi2 = ldtw(tw, 16 * kk);
+        cf hi2 = BBT_TW_SQUARE ? cmul(hi, hi) : ldtw(tw, 16 * kk);
         b[16] = cmul(b[16], hi2);
 #pragma unroll
         for (int r = 1; r < 8; ++r)
@@ -378,9 +382,10 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
     cf b[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) b[r] = v[q + r * NB];
-    if constexpr (LOG2NS > 0)
+    if constexpr (LOG2NS > 0) {
       // tw is the table of N-th roots of unity: exp(-2 pi i m / N), m < N.
       apply_twiddles<R>(b, tw, k << (C::LOG2N - LOG2NS - LOG2R));
+    }
     Dft<R>::run(b);
     if constexpr ((1 << (LOG2NS + LOG2R)) == C::N) {
 #pragma unroll

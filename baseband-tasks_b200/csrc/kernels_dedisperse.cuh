@@ -207,11 +207,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
 template <class C, int MODE>
 BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
   cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
-  const cf base = big.get((long long)k1 * t);
+  const cf base = cscale(big.get((long long)k1 * t), scale);
   pw[0] = big.get((long long)k1 * C::T);
 #pragma unroll
   for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
-  Ramp<C::LOG2E, MODE>::run(v, base, pw, scale);
+  Ramp<C::LOG2E, MODE>::run(v, base, pw);
 }
 
 // Pass 2 on one row per lane.  PLANAR: lanes are G consecutive rows
