@@ -1,6 +1,6 @@
 """Benchmark of the Dedisperse -> Channelize -> Power -> Integrate chain.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4|C5]
                     [--impl b200|reference]
 
 One step = one pass of the chain over one block of F overlap-save frames of
@@ -12,14 +12,17 @@ a synthetic NoiseGenerator stream:
   C4 (configs[3], the north-star target): (T, 2) complex64, 512 MHz at
      8192 MHz, Dedisperse(DM=1000, N=2^24) -> Channelize(1024) -> Power ->
      Integrate(1 ms).
+  C5 (configs[4]): the C4 stream -> Dedisperse -> Power -> Fold(512 bins,
+     polynomial phase), the folded profile summed over ranks with NCCL.
 
 ``value``: complex source samples (time x channel x polarization) per second
 through the public Task API with the input block resident in HBM.  ``e2e``:
 the same with the block in pinned host memory, copied to the device inside
-the timed region, and the integrated spectra copied back.  Timing: CUDA
-events, max over ranks.  With N > 1 every rank processes its own time block
-of the stream (time-block sharding with an overlap-save halo; no collective
-on this chain), so scaling is weak.
+the timed region (frame by frame on a copy stream, overlapped with the work
+on the frames that have arrived), and the integrated spectra copied back.
+Timing: CUDA events, max over ranks.  With N > 1 every rank processes its own
+time block of the stream (time-block sharding with an overlap-save halo; no
+collective on the Integrate chains), so scaling is weak.
 
 ``--impl reference`` times the reference's CPU path -- its numpy arithmetic
 restated in oracle/bbt_oracle.py, since the reference itself needs astropy and
@@ -383,7 +386,8 @@ def run_b200(args):
     value = samples_per_step * args.steps * world / (ms * 1e-3) / 1e9
     e2e = samples_per_step * args.steps * world / (ms_e2e * 1e-3) / 1e9
     mb = model_bytes(w)
-    cpu = cpu_baseline(w, budget_s=15.)
+    # The CPU baseline is timed on rank 0 of single-GPU runs only.
+    cpu = cpu_baseline(w, budget_s=15.) if world == 1 else None
     line = {
         'metric': ('Dedisperse->Power->Fold complex Gsamples/s' if folding
                    else 'Dedisperse->Channelize->Power->Integrate complex '
