@@ -101,6 +101,15 @@ struct Dft<8> {
   }
 };
 
+// s = a + w b and d = a - w b = 2 a - s for a constant w = (wr, wi): six
+// fused multiply-adds instead of a complex multiply and two additions.
+BBT_HD void fma_pm(cf a, cf b, float wr, float wi, cf& s, cf& d) {
+  s.x = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+  s.y = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+  d.x = fmaf(2.f, a.x, -s.x);
+  d.y = fmaf(2.f, a.y, -s.y);
+}
+
 template <>
 struct Dft<16> {
   static BBT_HD void run(cf* v) {
@@ -114,22 +123,48 @@ struct Dft<16> {
       for (int n1 = 0; n1 < 4; ++n1) a[n2][n1] = v[4 * n1 + n2];
       Dft<4>::run(a[n2]);
     }
-    // a[n2][k1] *= W16^{n2 k1}; W16^m = cos(m pi/8) - i sin(m pi/8).
-    a[1][1] = cmul(a[1][1], mk(c1, -s1));
-    a[1][2] = mk((a[1][2].x + a[1][2].y) * h, (a[1][2].y - a[1][2].x) * h);
-    a[1][3] = cmul(a[1][3], mk(s1, -c1));
-    a[2][1] = mk((a[2][1].x + a[2][1].y) * h, (a[2][1].y - a[2][1].x) * h);
-    a[2][2] = mul_mi(a[2][2]);
-    a[2][3] = mk((a[2][3].y - a[2][3].x) * h, -(a[2][3].x + a[2][3].y) * h);
-    a[3][1] = cmul(a[3][1], mk(s1, -c1));
-    a[3][2] = mk((a[3][2].y - a[3][2].x) * h, -(a[3][2].x + a[3][2].y) * h);
-    a[3][3] = cmul(a[3][3], mk(-c1, s1));  // W16^9
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) {
-      cf b[4] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1]};
+    // Second layer: X[k1 + 4 k2] = DFT4_n2( W16^{n2 k1} a[n2][k1] ), with the
+    // twiddles of n2 = 2 and n2 = 3 fused into the first additions.
+    // W16^m = (cos(m pi/8), -sin(m pi/8)).
+    {
+      cf b[4] = {a[0][0], a[1][0], a[2][0], a[3][0]};
       Dft<4>::run(b);
 #pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = b[k2];
+      for (int k2 = 0; k2 < 4; ++k2) v[4 * k2] = b[k2];
+    }
+    {  // k1 = 1: W16^1, W16^2, W16^3
+      cf s02, d02, s13, d13;
+      fma_pm(a[0][1], a[2][1], h, -h, s02, d02);
+      const cf b1 = cmul(a[1][1], mk(c1, -s1));
+      fma_pm(b1, a[3][1], s1, -c1, s13, d13);
+      d13 = mul_mi(d13);
+      v[1] = s02 + s13;
+      v[5] = d02 + d13;
+      v[9] = s02 - s13;
+      v[13] = d02 - d13;
+    }
+    {  // k1 = 2: W16^2, W16^4 = -i, W16^6
+      const cf b2 = mul_mi(a[2][2]);
+      const cf s02 = a[0][2] + b2, d02 = a[0][2] - b2;
+      const cf b1 = mk((a[1][2].x + a[1][2].y) * h, (a[1][2].y - a[1][2].x) * h);
+      cf s13, d13;
+      fma_pm(b1, a[3][2], -h, -h, s13, d13);
+      d13 = mul_mi(d13);
+      v[2] = s02 + s13;
+      v[6] = d02 + d13;
+      v[10] = s02 - s13;
+      v[14] = d02 - d13;
+    }
+    {  // k1 = 3: W16^3, W16^6, W16^9
+      cf s02, d02, s13, d13;
+      fma_pm(a[0][3], a[2][3], -h, -h, s02, d02);
+      const cf b1 = cmul(a[1][3], mk(s1, -c1));
+      fma_pm(b1, a[3][3], -c1, s1, s13, d13);
+      d13 = mul_mi(d13);
+      v[3] = s02 + s13;
+      v[7] = d02 + d13;
+      v[11] = s02 - s13;
+      v[15] = d02 - d13;
     }
   }
 };
@@ -181,15 +216,23 @@ struct Dft<32> {
                          0.19509032201612826785f};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      cf o;
-      if (k == 0)
-        o = od[0];
-      else if (k == 8)
-        o = mul_mi(od[8]);
-      else
-        o = cmul(od[k], mk(c[k], -s[k]));
-      v[k] = ev[k] + o;
-      v[k + 16] = ev[k] - o;
+      if (k == 0) {
+        v[0] = ev[0] + od[0];
+        v[16] = ev[0] - od[0];
+      } else if (k == 8) {
+        const cf o = mul_mi(od[8]);
+        v[8] = ev[8] + o;
+        v[24] = ev[8] - o;
+      } else {
+        // X = e + w o and X' = e - w o = 2 e - X, w = (c, -s), as six fused
+        // multiply-adds instead of a complex multiply and two additions.
+        const cf e = ev[k], o = od[k];
+        cf x;
+        x.x = fmaf(c[k], o.x, fmaf(s[k], o.y, e.x));
+        x.y = fmaf(c[k], o.y, fmaf(-s[k], o.x, e.y));
+        v[k] = x;
+        v[k + 16] = mk(fmaf(2.f, e.x, -x.x), fmaf(2.f, e.y, -x.y));
+      }
     }
   }
 };
