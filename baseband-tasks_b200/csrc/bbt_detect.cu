@@ -74,7 +74,11 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
   a.msub = msub;
   const int64_t blocks = ceil_div(msub * a.M, units);
   dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
-  const size_t smem = C::SMEM_BYTES;
+  // A second tile for asynchronous staging where it fits (see the kernel).
+  const bool stage =
+      INTEGRATE && C::SMEM_BYTES + (size_t)C::G * C::N * sizeof(cf) <= 200 * 1024;
+  const size_t smem =
+      C::SMEM_BYTES + (stage ? (size_t)C::G * C::N * sizeof(cf) : 0);
   auto kern = chanpow_kernel<C, INTEGRATE>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");

@@ -333,6 +333,23 @@ BBT_HD cf ld_stream(const cf* p) {
 #else
 #define BBT_LDGF(p) (*(p))
 #endif
+// Asynchronous 8-byte copy global -> shared (zeros when !valid), and the
+// wait for all copies this thread has issued.
+BBT_HD void cp_async8(cf* smem_dst, const cf* gmem_src, bool valid) {
+#if defined(__CUDA_ARCH__)
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst),
+               "l"(gmem_src), "r"(bytes));
+#else
+  *smem_dst = valid ? *gmem_src : mk(0.f, 0.f);
+#endif
+}
+BBT_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
 BBT_HD void prefetch_l2(const void* p) {
 #if defined(__CUDA_ARCH__)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

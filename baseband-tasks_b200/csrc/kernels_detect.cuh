@@ -111,27 +111,59 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
       acc[i].x = acc[i].y = acc[i].z = acc[i].w = 0.f;
   }
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  // When shared memory has room for a second tile, the next spectrum is
+  // copied in asynchronously (cp.async) while this one is transformed; each
+  // thread stages exactly the values it will consume itself.
+  constexpr bool STAGE =
+      INTEGRATE && C::SMEM_BYTES + (size_t)C::G * C::N * sizeof(cf) <= 200 * 1024;
+  cf* stage = smem + (C::SMEM_BYTES / sizeof(cf)) + (size_t)t * C::G + g;
+  const long long pstep = (long long)C::T * row;
+  if (STAGE && lo < hi) {
+    const long long j = lo + jsub;
+    const bool valid = lane_ok && j < hi;
+    const cf* pe = in + (j * C::N) * row + m * 2 + p + (long long)t * row;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      cp_async8(stage + e * (C::T * C::G), valid ? pe : in, valid);
+      pe += pstep;
+    }
+  }
   for (long long j0 = lo; j0 < hi; j0 += a.msub) {
     const long long j = j0 + jsub;
     const bool valid = lane_ok && j < hi;
     const cf* src = in + (j * C::N) * row + m * 2 + p;
     cf v[C::E];
-    const long long pstep = (long long)C::T * row;
-    {
-      const cf* pe = src + (long long)t * row;
+    if (STAGE) {
+      cp_async_wait();
 #pragma unroll
-      for (int e = 0; e < C::E; ++e) {
-        v[e] = valid ? ld_stream(pe) : mk(0.f, 0.f);
-        pe += pstep;
+      for (int e = 0; e < C::E; ++e) v[e] = stage[e * (C::T * C::G)];
+      if (j0 + a.msub < hi) {
+        const long long jn = j + a.msub;
+        const bool nvalid = lane_ok && jn < hi;
+        const cf* pe = src + a.msub * C::N * row + (long long)t * row;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) {
+          cp_async8(stage + e * (C::T * C::G), nvalid ? pe : in, nvalid);
+          pe += pstep;
+        }
       }
-    }
-    if (lane_ok && j + a.msub < hi && (g & 15) == 0) {
-      // Next spectrum of this lane group into L2 while this one is transformed.
-      const cf* pe = src + a.msub * C::N * row + (long long)t * row;
+    } else {
+      {
+        const cf* pe = src + (long long)t * row;
 #pragma unroll
-      for (int e = 0; e < C::E; ++e) {
-        prefetch_l2(pe);
-        pe += pstep;
+        for (int e = 0; e < C::E; ++e) {
+          v[e] = valid ? ld_stream(pe) : mk(0.f, 0.f);
+          pe += pstep;
+        }
+      }
+      if (lane_ok && j + a.msub < hi && (g & 15) == 0) {
+        // Next spectrum of this lane group into L2 meanwhile.
+        const cf* pe = src + a.msub * C::N * row + (long long)t * row;
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) {
+          prefetch_l2(pe);
+          pe += pstep;
+        }
       }
     }
     block_fft<C>(v, t, a.tw, sm);
