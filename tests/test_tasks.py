@@ -747,3 +747,45 @@ def test_pulse_stack(bt):
     avg.seek(100)
     np.testing.assert_allclose(avg.read(8), want[100:108] / 25, rtol=1e-6)
     assert abs((avg.time - src.start_time) - 108 * 125 / 1e4) < 1e-9
+
+
+# ------------------------------------------------------------- edge cases
+def test_ragged_and_odd_shapes(bt):
+    """Sample shapes that are not powers of two, reads into ``out``, streams
+    too short for a frame, and an integration start given as a time."""
+    rng = np.random.default_rng(51)
+    n = 3 * 4096
+    x = cnoise(rng, (n, 5))
+    freq = 300e6 + 1e6 * np.arange(5)
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=512,
+                         frequency=freq, sideband=np.array([1, -1, 1, 1, -1]))
+    dd = bt.Dedisperse(src, 1., samples_per_frame=2048 - 400)
+    op = orc.DispersePlan(-1., freq / 1e6, np.array([1, -1, 1, 1, -1]), 1.,
+                          True, n, 512, (5,), samples_per_frame=2048 - 400,
+                          fast_len=orc.next_pow2)
+    assert dd._ih_samples_per_frame == op.N
+    assert dd.samples_per_frame == op.samples_per_frame
+    want = orc.disperse(x, op)
+    out = np.empty((1000, 5), 'c8')
+    dd.seek(777)
+    assert dd.read(out=out) is out
+    assert_voltage(out, want[777:1777])
+    assert dd.tell() == 1777
+    sq = bt.Square(dd)
+    it = bt.Integrate(sq, 10, start=sq.start_time + 100.4e-6)   # a time
+    assert it._fused is None
+    got = it.read(5)
+    p = orc.square(want)
+    np.testing.assert_allclose(
+        got, p[100:150].reshape(5, 10, 5).mean(1), rtol=1e-5)
+    assert abs((it.start_time - sq.start_time) - 100.4e-6) < 1e-12
+    short = bt.ArrayStream(x[:1000], start_time(bt), 1e6, frequency=300e6,
+                           sideband=1)
+    with pytest.raises(AssertionError):
+        bt.Dedisperse(short, 1., samples_per_frame=2048 - 400)
+    with pytest.raises(AssertionError):
+        dd.read(out=np.empty((10, 4), 'c8'))
+    # Closing frees the plan; the stream cannot be read any more.
+    dd.close()
+    with pytest.raises(ValueError):
+        dd.read(1)
