@@ -215,13 +215,15 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
 }  // extern "C"
 namespace {
 template <int L>
-int launch_pfb(const PfbArgs& a, bool real, bbt_stream_t st) {
+int launch_pfb(const PfbArgs& a, int kind, bbt_stream_t st) {
   using D = DefaultCfg<L>;
   using C = FftCfg<L, D::LOG2E, 256>;
   const int64_t blocks = ceil_div(a.n_spec * a.inner, C::G);
   if (blocks > 2147483647LL) return fail(BBT_EUNSUPPORTED, "grid too large");
   const size_t smem = C::SMEM_BYTES;
-  auto kern = real ? pfb_kernel<C, true> : pfb_kernel<C, false>;
+  auto kern = kind == 2   ? pfb_kernel<C, 2>
+              : kind == 1 ? pfb_kernel<C, 1>
+                          : pfb_kernel<C, 0>;
   if (BBT_SET_SMEM(kern, smem))
     return fail(BBT_ECUDA, "cannot set shared memory size");
   prof_next_name = "pfb";
@@ -239,7 +241,8 @@ int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
     return fail(BBT_EUNSUPPORTED,
                 "polyphase filter bank needs a power-of-two number of "
                 "samples per spectrum in [2, 8192]");
-  if (n_tap < 1 || inner < 1) return fail(BBT_EINVAL, "bad filter bank shape");
+  if (n_tap < 1 || inner < 1 || is_real < 0 || is_real > 2)
+    return fail(BBT_EINVAL, "bad filter bank shape");
   if (n_spec <= 0) return BBT_OK;
   PfbArgs a;
   a.in = in;
@@ -250,7 +253,7 @@ int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
   a.n_spec = n_spec;
   a.n_tap = (int)n_tap;
   int rc = BBT_EUNSUPPORTED;
-#define F(L) rc = launch_pfb<L>(a, is_real != 0, as_stream(stream))
+#define F(L) rc = launch_pfb<L>(a, is_real, as_stream(stream))
   BBT_FOR_LOG2(ilog2(n), F)
 #undef F
   return rc;

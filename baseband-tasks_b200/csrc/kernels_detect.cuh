@@ -431,7 +431,7 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
 // Lanes are (spectrum, column) pairs with the column fastest; REAL input keeps
 // the n/2+1 non-negative frequencies (fourier/numpy.py:41-43).
 struct PfbArgs {
-  const void* in;     // [(n_spec + n_tap - 1) * n][inner] float or complex
+  const void* in;     // [(n_spec + n_tap - 1) * n][inner] int8, float or complex
   cf* out;            // [n_spec][n_chan][inner]
   const float* h;     // [n_tap][n]
   const cf* tw;
@@ -439,8 +439,10 @@ struct PfbArgs {
   int n_tap;
 };
 
-template <class C, bool REAL>
+// KIND: 0 complex64, 1 float32, 2 int8 (raw 8-bit samples, real).
+template <class C, int KIND>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
+  constexpr bool REAL = KIND != 0;
   cf* smem = BBT_SMEM(cf);
   const int tid = threadIdx.x;
   const int g = tid % C::G, t = tid / C::G;
@@ -458,7 +460,10 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
       for (int e = 0; e < C::E; ++e) {
         const int i = t + C::T * e;
         const float w = BBT_LDGF(h + i);
-        if (REAL) {
+        if (KIND == 2) {
+          v[e].x += w * (float)static_cast<const signed char*>(
+                            a.in)[base + i * a.inner];
+        } else if (KIND == 1) {
           v[e].x += w * static_cast<const float*>(a.in)[base + i * a.inner];
         } else {
           const cf x = static_cast<const cf*>(a.in)[base + i * a.inner];

@@ -75,9 +75,13 @@ class PolyphaseFilterBankSamples(TaskBase):
         self._n_tap = n_tap
         self._response = response
         self._d_response = None
-        self._real = np.dtype(ih.dtype).kind == 'f'
+        # 0 complex, 1 float, 2 raw 8-bit integer samples (kept as int8 on
+        # the device: a quarter of the bytes to copy and read).
+        kind = np.dtype(ih.dtype).kind
+        self._real = 2 if np.dtype(ih.dtype) == np.int8 else int(kind != 'c')
+        fft_dtype = np.float32 if self._real == 2 else ih.dtype
         self._FFT = fft_maker.get()
-        self._fft = self._FFT((spf, n) + tuple(ih.sample_shape), ih.dtype,
+        self._fft = self._FFT((spf, n) + tuple(ih.sample_shape), fft_dtype,
                               axis=1, sample_rate=ih.sample_rate)
 
         frequency = getattr_if_none(ih, 'frequency', frequency, required=False)
@@ -108,8 +112,8 @@ class PolyphaseFilterBankSamples(TaskBase):
         """Filter and transform all complete spectra in ``data``."""
         lib = _cabi.lib()
         host = not B.is_tensor(data)
-        x = B.as_device(data, dtype=np.float32 if self._real
-                        else np.complex64)
+        x = B.as_device(data, dtype=(np.complex64, np.float32,
+                                     np.int8)[self._real])
         if self._d_response is None:
             self._d_response = B.as_device(
                 np.ascontiguousarray(self._response, dtype=np.float32))

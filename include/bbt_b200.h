@@ -151,7 +151,7 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
  * PolyphaseFilterBankSamples.ppf (pfb.py:91-100; PolyphaseFilterBank.ppf
  * :145-154 computes the same in the Fourier domain) followed by
  * Channelize.task (channelize.py:73-74).  in: [(n_spec + n_tap - 1) * n][inner]
- * float32 (is_real) or complex64; response: device float32 [n_tap][n];
+ * complex64 (is_real = 0), float32 (1) or raw int8 samples (2); response: device float32 [n_tap][n];
  * out: [n_spec][n_chan][inner] complex64 with n_chan = n/2+1 (real) or n. */
 int bbt_pfb_exec(const void* in, void* out, const void* response, int64_t n,
                  int64_t n_tap, int64_t inner, int64_t n_spec, int is_real,

@@ -592,6 +592,15 @@ def test_polyphase_filter_bank(bt, dtype, shape):
     pfb2 = bt.PolyphaseFilterBank(src, response, samples_per_frame=5)
     assert pfb2.samples_per_frame == 5
     assert_voltage(pfb2.read(), want[:pfb2.shape[0]].astype('c8'))
+    if dtype == 'f4' and shape:
+        # Raw 8-bit samples stay int8 on the device.
+        xi = np.clip(np.round(x * 30), -127, 127).astype('i1')
+        si = bt.ArrayStream(xi, start_time(bt), 1e6, samples_per_frame=128,
+                            frequency=300e6, sideband=1)
+        pi = bt.PolyphaseFilterBank(si, response)
+        wi = orc.pfb(xi.astype('f8'), response, ih_samples_per_frame=128)
+        assert pi.dtype == np.complex64 and pi.shape == wi.shape
+        assert_voltage(pi.read(), wi.astype('c8'))
 
 
 def test_integrate_over_phase(bt):
