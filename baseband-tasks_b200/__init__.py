@@ -25,4 +25,5 @@ from .functions import Square, Power  # noqa: F401
 from .integration import (Integrate, Fold, PulseStack,  # noqa: F401
                           PolynomialPhase)
 from .generators import (StreamGenerator, EmptyStreamGenerator, Noise,  # noqa
-                         NoiseGenerator, ArrayStream)
+                         NoiseGenerator, ArrayStream, PayloadStream,
+                         payload_levels, encode_payload)

@@ -12,7 +12,9 @@ from ctypes import (POINTER, c_char_p, c_double, c_int, c_int8, c_int32,
 __all__ = ['CABI', 'BBTError', 'lib', 'device', 'check']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libbbt_b200.so')
+# BBT_B200_LIB selects another build of the same CUDA library (kernel A/B runs).
+LIB_PATH = os.environ.get('BBT_B200_LIB') or os.path.join(
+    _HERE, 'csrc', 'libbbt_b200.so')
 
 BBT_C2C, BBT_R2C, BBT_C2R = 0, 1, 2
 BBT_FORWARD, BBT_BACKWARD = 0, 1
@@ -63,6 +65,8 @@ _SIGNATURES = {
     'bbt_shift_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                c_int, c_void_p]),
     'bbt_convert_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'bbt_decode_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                c_void_p]),
     'bbt_average_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int64, c_void_p]),
     'bbt_launch_count': (c_int64, []),

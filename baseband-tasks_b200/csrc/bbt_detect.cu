@@ -294,6 +294,21 @@ int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
   return check_launch("conversion kernel");
 }
 
+int bbt_decode_exec(const void* in, void* out, const float* levels, int64_t n,
+                    int bps, void* stream) {
+  if (!in || !out || !levels) return fail(BBT_EINVAL, "null argument");
+  if (bps != 1 && bps != 2 && bps != 4 && bps != 8)
+    return fail(BBT_EUNSUPPORTED, "bits per sample must be 1, 2, 4 or 8");
+  if (reinterpret_cast<uintptr_t>(out) & 15)
+    return fail(BBT_EINVAL, "decode output must be 16-byte aligned");
+  if (n <= 0) return BBT_OK;
+  BBT_LAUNCH(decode_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256),
+             256 * sizeof(float), as_stream(stream),
+             static_cast<const unsigned char*>(in), static_cast<float*>(out),
+             levels, (long long)n, bps);
+  return check_launch("decode kernel");
+}
+
 int bbt_average_exec(const void* sum, const void* count, void* out,
                      int64_t n_bins, int64_t inner, void* stream) {
   if (!sum || !count || !out) return fail(BBT_EINVAL, "null argument");

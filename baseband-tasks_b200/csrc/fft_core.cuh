@@ -386,7 +386,9 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 }
 
 #ifndef BBT_TW_SQUARE
-#define BBT_TW_SQUARE 1  // powers of two by squaring instead of look-ups
+// 1: powers of two of the twiddle by squaring instead of look-ups; 2: w^8 and
+// w^16 looked up (less rounding error, two more loads); 0: all looked up.
+#define BBT_TW_SQUARE 1
 #endif
 // b[r] *= w^r for r < R, with w = tw[kk]: powers of two are looked up, the
 // others are products of two looked-up or derived values.
@@ -409,12 +411,12 @@ BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
 #pragma unroll
     for (int r = 1; r < LOW; ++r) b[r] = cmul(b[r], w[r]);
     if constexpr (R >= 16) {
-      cf hi = BBT_TW_SQUARE ? cmul(w[4], w[4]) : ldtw(tw, 8 * kk);
+      cf hi = BBT_TW_SQUARE == 1 ? cmul(w[4], w[4]) : ldtw(tw, 8 * kk);
       b[8] = cmul(b[8], hi);
 #pragma unroll
       for (int r = 1; r < 8; ++r) b[8 + r] = cmul(b[8 + r], cmul(hi, w[r]));
       if constexpr (R >= 32) {
-        cf hi2 = BBT_TW_SQUARE ? cmul(hi, hi) : ldtw(tw, 16 * kk);
+        cf hi2 = BBT_TW_SQUARE == 1 ? cmul(hi, hi) : ldtw(tw, 16 * kk);
         b[16] = cmul(b[16], hi2);
 #pragma unroll
         for (int r = 1; r < 8; ++r)

@@ -204,13 +204,28 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
 // (MODE 0) or by its conjugate and the scale (MODE 1: v <- conj(v w) scale),
 // generated as base * step^e from two table look-ups.  Called before and
 // after the transforms rather than keeping the powers in registers.
+#ifndef BBT_RAMP_SQUARE
+// 1: powers of the ramp step by squaring (fastest; each squaring doubles the
+// rounding error of the step).  0: every power from the table.  Measured on
+// a 2^24-point dedispersion (tools/accuracy.py): RMS error 1.3e-6 of the RMS
+// with squaring here and in apply_twiddles, 4.3e-7 with BBT_RAMP_SQUARE=0 and
+// BBT_TW_SQUARE=2 at 3 % less throughput (numpy's single-precision path:
+// 1.9e-7; the parity tolerance is 1e-5).
+#define BBT_RAMP_SQUARE 1
+#endif
 template <class C, int MODE>
 BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
   cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
   const cf base = cscale(big.get((long long)k1 * t), scale);
+#if BBT_RAMP_SQUARE
   pw[0] = big.get((long long)k1 * C::T);
 #pragma unroll
   for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
+#else
+#pragma unroll
+  for (int b = 0; b < C::LOG2E; ++b)
+    pw[b] = big.get(((long long)k1 * C::T) << b);
+#endif
   Ramp<C::LOG2E, MODE>::run(v, base, pw);
 }
 

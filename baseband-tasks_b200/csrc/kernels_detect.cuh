@@ -515,6 +515,42 @@ BBT_GLOBAL void complex_to_real_kernel(const cf* BBT_RESTRICT in,
     out[i] = in[i].x;
 }
 
+// Packed payload decode: value v occupies bits [v*bps, (v+1)*bps) of the byte
+// stream (first value in the least significant bits) and maps to levels[code].
+// One thread per four output values, so stores are full float4 lines.
+BBT_GLOBAL void decode_kernel(const unsigned char* BBT_RESTRICT in,
+                              float* BBT_RESTRICT out,
+                              const float* BBT_RESTRICT levels, long long n,
+                              int bps) {
+  float* lut = BBT_SMEM(float);
+  for (int i = threadIdx.x; i < (1 << bps); i += blockDim.x) lut[i] = levels[i];
+  BBT_SYNC();
+  const unsigned mask = (1u << bps) - 1u;
+  const long long n_bytes = (n * bps + 7) >> 3;
+  const long long n4 = (n + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long bit = q * 4 * bps;
+    const long long b0 = bit >> 3;
+    const int sh = (int)(bit & 7);
+    const int nb = (sh + 4 * bps + 7) >> 3;
+    unsigned long long w = 0;
+    for (int k = 0; k < nb; ++k)
+      if (b0 + k < n_bytes) w |= (unsigned long long)in[b0 + k] << (8 * k);
+    w >>= sh;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = lut[(unsigned)(w >> (k * bps)) & mask];
+    if (q * 4 + 4 <= n) {
+      float4 o;
+      o.x = v[0], o.y = v[1], o.z = v[2], o.w = v[3];
+      *reinterpret_cast<float4*>(out + q * 4) = o;
+    } else {
+      for (int k = 0; q * 4 + k < n; ++k) out[q * 4 + k] = v[k];
+    }
+  }
+}
+
 // out[b][c] = sum[b][c] / count[b]; 0/0 gives NaN like numpy's division.
 BBT_GLOBAL void average_kernel(const float* BBT_RESTRICT sum,
                                const unsigned long long* BBT_RESTRICT count,

@@ -7,14 +7,18 @@ and the stream is seekable) and `NoiseGenerator` (:193-245).  These run on the
 host (they are inputs, not part of the accelerated path).  `ArrayStream` is
 new: it presents an array -- in particular a tensor already resident in HBM --
 as a stream, so a chain can be fed without any host round trip.
+`PayloadStream` is new too: a packed 1/2/4/8-bit baseband payload that is
+copied to the GPU as bytes and decoded there.
 """
 import numpy as np
 
 from . import _buffers as B
+from . import _cabi
 from .base import Base
 
 __all__ = ['StreamGenerator', 'EmptyStreamGenerator',
-           'Noise', 'NoiseGenerator', 'ArrayStream']
+           'Noise', 'NoiseGenerator', 'ArrayStream', 'PayloadStream',
+           'payload_levels', 'encode_payload']
 
 
 class StreamGenerator(Base):
@@ -118,3 +122,129 @@ class ArrayStream(Base):
     def close(self):
         super().close()
         self._data = None
+
+
+# Decoder levels of the VDIF-style encodings in the `baseband` package, which
+# the reference's coded HDF5 payloads reuse (io/hdf5/payload.py:165-166).
+# `baseband` is not vendored with the reference, so these defaults are a
+# restatement from its documentation (parity unpinned); any table of
+# 1 << bps levels can be passed instead.
+_OPTIMAL_2BIT_HIGH = 3.316505
+_FOUR_BIT_1_SIGMA = 2.95
+
+
+def payload_levels(bps):
+    """Default float32 value of each ``bps``-bit code."""
+    if bps == 1:
+        levels = [-1., 1.]
+    elif bps == 2:
+        levels = [-_OPTIMAL_2BIT_HIGH, -1., 1., _OPTIMAL_2BIT_HIGH]
+    elif bps == 4:
+        levels = (np.arange(16) - 8.) / _FOUR_BIT_1_SIGMA
+    elif bps == 8:
+        levels = np.arange(256) - 127.5    # 0..255 encode -127.5..127.5
+    else:
+        raise NotImplementedError("bits per sample must be 1, 2, 4 or 8")
+    return np.asarray(levels, dtype=np.float32)
+
+
+def encode_payload(data, bps, levels=None):
+    """Pack samples into ``bps``-bit codes (nearest level), as uint8 bytes.
+
+    Host-side helper for tests and benchmarks: the first value goes in the
+    least significant bits; complex samples are (re, im) value pairs.
+    """
+    levels = payload_levels(bps) if levels is None else np.asarray(levels)
+    data = np.ascontiguousarray(data)
+    if data.dtype.kind == 'c':
+        data = data.view(data.real.dtype)
+    values = data.reshape(-1)
+    order = np.argsort(levels)
+    sorted_levels = levels[order]
+    edges = (sorted_levels[1:] + sorted_levels[:-1]) / 2
+    codes = order[np.searchsorted(edges, values)].astype(np.uint8)
+    per_byte = 8 // bps
+    pad = -len(codes) % per_byte
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, np.uint8)])
+    codes = codes.reshape(-1, per_byte)
+    shifts = (np.arange(per_byte) * bps).astype(np.uint8)
+    return np.bitwise_or.reduce(codes << shifts, axis=1).astype(np.uint8)
+
+
+class PayloadStream(Base):
+    """A packed baseband payload presented as a stream, decoded on the GPU.
+
+    ``words`` holds ``bps``-bit codes (any integer dtype, used as bytes; first
+    value in the least significant bits), time-major over ``sample_shape``
+    with complex samples stored as (re, im) pairs.  Only the packed bytes
+    cross PCIe; `bbt_decode_exec` expands them to float32/complex64 in HBM.
+    """
+
+    def __init__(self, words, bps, sample_shape, start_time, sample_rate,
+                 samples_per_frame=None, complex_data=False, levels=None,
+                 **kwargs):
+        if bps not in (1, 2, 4, 8):
+            raise NotImplementedError("bits per sample must be 1, 2, 4 or 8")
+        if B.is_tensor(words):
+            self._words = words.contiguous().view(B.torch_dtype(np.uint8))
+            n_bytes = self._words.numel()
+        else:
+            self._words = np.ascontiguousarray(words).reshape(-1).view(np.uint8)
+            n_bytes = self._words.size
+        self.bps = bps
+        sample_shape = tuple(sample_shape)
+        self._values_per_sample = (int(np.prod(sample_shape, dtype=np.int64))
+                                   * (2 if complex_data else 1))
+        n_sample = n_bytes * 8 // (bps * self._values_per_sample)
+        if samples_per_frame is None:
+            samples_per_frame = n_sample
+        levels = payload_levels(bps) if levels is None else np.asarray(
+            levels, dtype=np.float32)
+        if levels.shape != (1 << bps,):
+            raise ValueError("need one level for each of the 1 << bps codes")
+        self._levels = levels
+        self._d_levels = None
+        super().__init__(shape=(n_sample,) + sample_shape,
+                         start_time=start_time, sample_rate=sample_rate,
+                         samples_per_frame=samples_per_frame,
+                         dtype=np.complex64 if complex_data else np.float32,
+                         **kwargs)
+
+    def _decode(self, start, count):
+        bit0 = start * self._values_per_sample * self.bps
+        if bit0 % 8:
+            raise ValueError("read does not start on a byte of the payload")
+        n = count * self._values_per_sample
+        words = B.as_device(
+            self._words[bit0 // 8:(bit0 + n * self.bps + 7) // 8])
+        if self._d_levels is None:
+            self._d_levels = B.as_device(self._levels)
+        out = B.empty((n,), np.float32)
+        lib = _cabi.lib()
+        lib.check(lib.bbt_decode_exec(B.ptr(words), B.ptr(out),
+                                      B.ptr(self._d_levels), n, self.bps,
+                                      _cabi.stream_ptr()))
+        if self.complex_data:
+            out = B.torch().view_as_complex(out.view(-1, 2))
+        return out.view((count,) + self.sample_shape)
+
+    def _read_data(self, count, out=None):
+        start = self.offset
+        if (start * self._values_per_sample * self.bps) % 8:
+            return super()._read_data(count, out)   # frame by frame
+        data = self._decode(start, count)
+        self.offset = start + count
+        if out is not None:
+            out[...] = data if B.is_tensor(out) else B.as_host(data)
+            return out
+        return data
+
+    def _read_frame(self, frame_index):
+        start = frame_index * self.samples_per_frame
+        return self._decode(start, min(self.samples_per_frame,
+                                       self.shape[0] - start))
+
+    def close(self):
+        super().close()
+        self._words = None

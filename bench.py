@@ -387,7 +387,8 @@ def run_b200(args):
     e2e = samples_per_step * args.steps * world / (ms_e2e * 1e-3) / 1e9
     mb = model_bytes(w)
     # The CPU baseline is timed on rank 0 of single-GPU runs only.
-    cpu = cpu_baseline(w, budget_s=15.) if world == 1 else None
+    cpu = (cpu_baseline(w, budget_s=15.)
+           if world == 1 and not args.no_cpu else None)
     line = {
         'metric': ('Dedisperse->Power->Fold complex Gsamples/s' if folding
                    else 'Dedisperse->Channelize->Power->Integrate complex '
@@ -553,6 +554,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true',
+                    help='skip the CPU baseline leg (kernel A/B runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

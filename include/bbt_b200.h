@@ -173,6 +173,16 @@ int bbt_shift_exec(const void* in, void* out, const int64_t* offset,
 int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
                      void* stream);
 
+/* ---- Packed payload decode (the VDIF-style encodings of baseband, which the
+ * reference's coded HDF5 payloads reuse, io/hdf5/payload.py:165-166): value v
+ * is the bps-bit code at bits [v*bps, (v+1)*bps) of the byte stream `in`
+ * (first value in the least significant bits); out[v] = levels[code], with
+ * levels a device table of 1 << bps float32.  bps in {1, 2, 4, 8}; complex
+ * samples are (re, im) value pairs, so out can be viewed as complex64.
+ * out must be 16-byte aligned. */
+int bbt_decode_exec(const void* in, void* out, const float* levels, int64_t n,
+                    int bps, void* stream);
+
 /* ---- Averaging: out[b][c] = sum[b][c] / count[b] (NaN for empty bins),
  * the division Integrate._read_frame does (integration.py:268-269). */
 int bbt_average_exec(const void* sum, const void* count, void* out,

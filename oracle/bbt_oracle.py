@@ -516,3 +516,19 @@ def fold(x, offsets, n_phase, phase_of_sample, searchsorted_side='left'):
     np.add.at(data, (tbin, pbin), x[offsets[0]:offsets[-1]])
     np.add.at(count, (tbin, pbin), 1)
     return data, count
+
+
+# --------------------------------------------------------------------------
+# Packed payloads.  PARITY UNPINNED: the decoding
+# lives in the third-party `baseband` package (VDIFPayload._decoders, reused
+# by io/hdf5/payload.py:165-166), which is not vendored with the reference and
+# is absent here.  This restates its documented VDIF convention: bps-bit
+# codes, the first value in the least significant bits of each byte, mapped
+# through a table of levels.
+def decode_payload(words, bps, levels, n=None):
+    """Values of the ``bps``-bit codes in the byte stream ``words``."""
+    b = np.ascontiguousarray(words).reshape(-1).view(np.uint8)
+    shifts = np.arange(0, 8, bps)
+    codes = ((b[:, np.newaxis] >> shifts) & ((1 << bps) - 1)).reshape(-1)
+    values = np.asarray(levels)[codes]
+    return values if n is None else values[:n]

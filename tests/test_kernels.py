@@ -453,3 +453,25 @@ def test_fold(backend, power, n_phase, n_tbin):
         pass
     np.testing.assert_array_equal(got_cnt, wcount.reshape(n_tbin, n_phase))
     assert_power(backend.to_host(d_sum), want)
+
+
+@pytest.mark.parametrize('bps', [1, 2, 4, 8])
+@pytest.mark.parametrize('n', [1, 13, 4096, 100003])
+def test_decode(backend, bps, n):
+    """Packed payload decode; exact table look-ups."""
+    rng = np.random.default_rng(bps * 1000 + n)
+    words = rng.integers(0, 256, (n * bps + 7) // 8, dtype=np.uint8)
+    levels = rng.normal(size=1 << bps).astype('f4')
+    d_w = backend.to_dev(words)
+    d_l = backend.to_dev(levels)
+    d_out = backend.empty((n,), 'f4')
+    backend.lib.check(backend.lib.bbt_decode_exec(
+        backend.ptr(d_w), backend.ptr(d_out), backend.ptr(d_l), n, bps,
+        backend.stream))
+    backend.sync()
+    np.testing.assert_array_equal(backend.to_host(d_out),
+                                  orc.decode_payload(words, bps, levels, n))
+    with pytest.raises(NotImplementedError):
+        backend.lib.check(backend.lib.bbt_decode_exec(
+            backend.ptr(d_w), backend.ptr(d_out), backend.ptr(d_l), n, 3,
+            backend.stream))
