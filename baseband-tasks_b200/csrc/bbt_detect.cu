@@ -193,21 +193,31 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
   a.b_first = b_first;
   a.i_ref = i_ref;
   a.rate = rate;
+  {
+    // The reciprocal shortcut needs a normal rate whose significand is not
+    // all ones (the one case outside Markstein's theorem).
+    uint64_t bits;
+    memcpy(&bits, &rate, 8);
+    const bool all_ones = (bits & 0xfffffffffffffULL) == 0xfffffffffffffULL;
+    a.inv_rate = (std::isnormal(rate) && rate > 0. && !all_ones) ? 1. / rate : 0.;
+  }
   a.ncoef = pbin ? 1 : ncoef;
   for (int k = 0; k < 8; ++k) a.coef[k] = (!pbin && k < ncoef) ? coef[k] : 0.;
   a.n_phase = n_phase;
   const size_t smem = (size_t)n_phase * (inner + 1) * 4;
   a.use_smem = smem <= 40 * 1024;
+  if (a.use_smem && inner == 4 && !(reinterpret_cast<uintptr_t>(in) & 15))
+    a.use_smem = 2;
   const int64_t chunks = std::max<int64_t>(
       1, std::min<int64_t>(ceil_div((int64_t)sm_count() * 8, n_bins),
                            ceil_div(n, n_bins * 1024)));
   dim3 grid((unsigned)chunks, (unsigned)n_bins);
   prof_next_name = "fold";
   if (power)
-    BBT_LAUNCH(fold_kernel<true>, grid, dim3(256), a.use_smem ? smem : 0,
+    BBT_LAUNCH(fold_kernel<true>, grid, dim3(kFoldThreads), a.use_smem ? smem : 0,
                as_stream(stream), a);
   else
-    BBT_LAUNCH(fold_kernel<false>, grid, dim3(256), a.use_smem ? smem : 0,
+    BBT_LAUNCH(fold_kernel<false>, grid, dim3(kFoldThreads), a.use_smem ? smem : 0,
                as_stream(stream), a);
   return check_launch("fold kernel");
 }

@@ -259,10 +259,12 @@ struct FoldArgs {
   long long b_first;          // time bin of blockIdx.y = 0
   double i_ref;               // sample index (may be fractional) at which dt = 0
   double rate;
+  double inv_rate;            // RN(1 / rate), or 0 to divide (see fold_phase_bin_fast)
   double coef[8];
   int ncoef;
   int n_phase;
   int use_smem;               // privatise the profile in shared memory
+                              // (2: and take the four-values-per-sample path)
 };
 
 BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
@@ -281,6 +283,149 @@ BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
 // per-warp accumulator that is only flushed (one atomic per value) when the
 // bin changes.  Mixed warps fall back to one shared-memory atomic per sample.
 constexpr int kFoldFast = 8;  // most values per sample kept in registers
+constexpr int kFoldUnroll = 4;  // samples in flight per thread (4 values each)
+constexpr int kFoldThreads = 256;
+
+#if defined(__CUDA_ARCH__)
+// Phase bin of absolute sample index xi (already a double; exact below 2^53),
+// the same arithmetic as fold_phase_bin with two shortcuts that do not change
+// a single bit: the division by the sample rate is done with the correctly
+// rounded reciprocal y = RN(1 / rate) and two Newton corrections in FMA
+// arithmetic (Markstein: with y correctly rounded and q1 faithful,
+// RN(q1 + RN(x - q1 rate) y) is the correctly rounded quotient), and the
+// Horner recurrence always runs its last four steps, starting from zero
+// (0 * dt + c is exactly c, so missing high coefficients change nothing).
+struct FoldPhase {
+  double i_ref, rate, inv_rate, c0, c1, c2, c3, n_phase;
+};
+BBT_DEV int fold_phase_bin_fast(const FoldArgs& a, const FoldPhase& f, double xi) {
+  const double x = dadd(xi, -f.i_ref);
+  double dt;
+  if (f.inv_rate != 0.) {
+    const double q0 = dmul(x, f.inv_rate);
+    const double q1 = __fma_rn(__fma_rn(-q0, f.rate, x), f.inv_rate, q0);
+    dt = __fma_rn(__fma_rn(-q1, f.rate, x), f.inv_rate, q1);
+  } else {
+    dt = ddiv(x, f.rate);
+  }
+  double ph = 0.;
+  for (int k = a.ncoef - 1; k >= 4; --k) ph = dadd(dmul(ph, dt), a.coef[k]);
+  ph = dadd(dmul(ph, dt), f.c3);
+  ph = dadd(dmul(ph, dt), f.c2);
+  ph = dadd(dmul(ph, dt), f.c1);
+  ph = dadd(dmul(ph, dt), f.c0);
+  double r = dadd(ph, -trunc(ph));
+  if (r < 0.) r = dadd(r, 1.0);
+  int q = (int)dmul(r, f.n_phase);
+  q = q < 0 ? 0 : q;
+  return q >= a.n_phase ? a.n_phase - 1 : q;
+}
+
+// Four values per sample (the Stokes-like products of one polarization pair,
+// or four floats).  Each thread has kFoldUnroll samples in flight so that DRAM
+// latency is covered; a warp whose 32 samples share a phase bin reduces its
+// 128 values with six shuffles (lanes trade halves, then quarters, of their
+// values before the plain butterfly), leaving component c in the lanes with
+// (lane >> 3) == c, where it is kept in a running sum until the bin changes.
+template <bool POWER, bool CHECK>
+BBT_DEV void fold_four_tile(const FoldArgs& a, const FoldPhase& f, float* hist,
+                            unsigned* hcnt, long long ib, long long i1, double xd,
+                            int lane, float& acc, unsigned& acc_n, int& cur) {
+  const unsigned full = 0xffffffffu;
+  const int comp = lane >> 3;
+  const bool flusher = (lane & 7) == 0;
+  f4 x[kFoldUnroll];
+  int p[kFoldUnroll];
+#pragma unroll
+  for (int u = 0; u < kFoldUnroll; ++u) {
+    const long long i = ib + u * kFoldThreads + lane;
+    x[u].x = x[u].y = x[u].z = x[u].w = 0.f;
+    if (!CHECK || i < i1) {
+      const float4 q = __ldcs(static_cast<const float4*>(a.in) + i);
+      x[u].x = q.x, x[u].y = q.y, x[u].z = q.z, x[u].w = q.w;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kFoldUnroll; ++u) {
+    const long long i = ib + u * kFoldThreads + lane;
+    p[u] = -1;
+    if (!CHECK || i < i1) {
+      if (a.pbin) {
+        int q = a.pbin[i];
+        q = q < 0 ? 0 : q;
+        p[u] = q >= a.n_phase ? a.n_phase - 1 : q;
+      } else {
+        p[u] = fold_phase_bin_fast(a, f, xd + (double)(u * kFoldThreads));
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kFoldUnroll; ++u) {
+    if (CHECK && ib + u * kFoldThreads >= i1) break;  // warp-uniform
+    f4 v = x[u];
+    if (POWER) {
+      cf xa, xb;
+      xa.x = v.x, xa.y = v.y, xb.x = v.z, xb.y = v.w;
+      v = stokes_like(xa, xb);
+    }
+    const int p0 = __shfl_sync(full, p[u], 0);
+    if (__all_sync(full, p[u] == p0)) {
+      const bool up = lane & 16;
+      float k0 = up ? v.z : v.x, k1 = up ? v.w : v.y;
+      k0 += __shfl_xor_sync(full, up ? v.x : v.z, 16);
+      k1 += __shfl_xor_sync(full, up ? v.y : v.w, 16);
+      const bool up2 = lane & 8;
+      float k = up2 ? k1 : k0;
+      k += __shfl_xor_sync(full, up2 ? k0 : k1, 8);
+      k += __shfl_xor_sync(full, k, 4);
+      k += __shfl_xor_sync(full, k, 2);
+      k += __shfl_xor_sync(full, k, 1);
+      if (p0 != cur) {
+        if (cur >= 0 && flusher) {
+          atomicAdd(hist + cur * 4 + comp, acc);
+          if (lane == 0) atomicAdd(hcnt + cur, acc_n);
+        }
+        cur = p0;
+        acc = 0.f;
+        acc_n = 0;
+      }
+      acc += k;
+      acc_n += 32;
+    } else if (p[u] >= 0) {
+      atomicAdd(hist + p[u] * 4 + 0, v.x);
+      atomicAdd(hist + p[u] * 4 + 1, v.y);
+      atomicAdd(hist + p[u] * 4 + 2, v.z);
+      atomicAdd(hist + p[u] * 4 + 3, v.w);
+      atomicAdd(hcnt + p[u], 1u);
+    }
+  }
+}
+
+template <bool POWER>
+BBT_DEV void fold_four(const FoldArgs& a, float* hist, unsigned* hcnt,
+                       long long i0, long long i1) {
+  const int lane = threadIdx.x & 31;
+  FoldPhase f;
+  f.i_ref = a.i_ref, f.rate = a.rate, f.inv_rate = a.inv_rate;
+  f.c0 = a.coef[0], f.c1 = a.coef[1], f.c2 = a.coef[2], f.c3 = a.coef[3];
+  f.n_phase = (double)a.n_phase;
+  float acc = 0.f;
+  unsigned acc_n = 0;
+  int cur = -1;
+  constexpr long long step = (long long)kFoldThreads * kFoldUnroll;
+  long long ib = i0 + (threadIdx.x - lane);
+  // Sample indices as doubles: integers below 2^53 add exactly.
+  double xd = (double)(a.i_first + ib + lane);
+  for (; ib + step - kFoldThreads + 32 <= i1; ib += step, xd += (double)step)
+    fold_four_tile<POWER, false>(a, f, hist, hcnt, ib, i1, xd, lane, acc, acc_n, cur);
+  if (ib < i1)
+    fold_four_tile<POWER, true>(a, f, hist, hcnt, ib, i1, xd, lane, acc, acc_n, cur);
+  if (cur >= 0 && (lane & 7) == 0) {
+    atomicAdd(hist + cur * 4 + (lane >> 3), acc);
+    if (lane == 0) atomicAdd(hcnt + cur, acc_n);
+  }
+}
+#endif
 
 template <bool POWER>
 BBT_GLOBAL void fold_kernel(FoldArgs a) {
@@ -304,7 +449,9 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
   unsigned long long* gcnt = a.count + b * a.n_phase;
   const long long width = POWER ? a.inner / 4 : a.inner;  // input items per sample
 #if defined(__CUDA_ARCH__)
-  if (a.use_smem && a.inner <= kFoldFast) {
+  if (a.use_smem == 2) {
+    fold_four<POWER>(a, hist, hcnt, i0, i1);
+  } else if (a.use_smem && a.inner <= kFoldFast) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     float acc[kFoldFast];

@@ -161,8 +161,18 @@ def encode_payload(data, bps, levels=None):
     values = data.reshape(-1)
     order = np.argsort(levels)
     sorted_levels = levels[order]
-    edges = (sorted_levels[1:] + sorted_levels[:-1]) / 2
-    codes = order[np.searchsorted(edges, values)].astype(np.uint8)
+    edges = ((sorted_levels[1:] + sorted_levels[:-1]) / 2).astype(values.dtype)
+    codes = np.empty(len(values), np.uint8)
+    chunk = 1 << 24              # bounds the int64 temporaries
+    steps = np.diff(levels.astype(np.float64))
+    uniform = len(levels) > 2 and np.allclose(steps, steps[0]) and steps[0] > 0
+    for i in range(0, len(values), chunk):
+        v = values[i:i + chunk]
+        if uniform:      # evenly spaced, increasing levels: round
+            c = np.rint((v - levels[0]) * values.dtype.type(1. / steps[0]))
+            codes[i:i + chunk] = np.clip(c, 0, len(levels) - 1)
+        else:
+            codes[i:i + chunk] = order[np.searchsorted(edges, v)]
     per_byte = 8 // bps
     pad = -len(codes) % per_byte
     if pad:

@@ -455,6 +455,47 @@ def test_fold(backend, power, n_phase, n_tbin):
     assert_power(backend.to_host(d_sum), want)
 
 
+@pytest.mark.parametrize('rate,coef,i_first', [
+    (512e6, [0.1, 641.234567, -1.5e-3], 0),
+    (1e6 / 3 + 0.123, [-5.3, -77.7, 0.01, 1e-4, -2e-6, 3e-8], 10 ** 12),
+    (float(np.nextafter(8e6, 0)), [1e5 + 0.7, 200.25], 123456789),
+    (33554432., [0., 1000.], 0),
+])
+def test_fold_phase_bins_exact(backend, rate, coef, i_first):
+    """Phase bins are bit-exact with the float64 evaluation of the oracle for
+    awkward rates, long polynomials, negative phases and large sample
+    indices (the kernel divides through a reciprocal and pads the Horner
+    recurrence; neither may change a bit)."""
+    n = 3000000 if backend.big else 40000
+    n_phase = 128
+    coef = np.array(coef)
+    i_ref = i_first + 1000.5
+    rng = np.random.default_rng(17)
+    x = rng.normal(size=(n, 4)).astype('f4')
+    i = i_first + np.arange(n, dtype=np.int64)
+    pbin = ((poly_phase(coef, i, i_ref, rate) % 1.) * n_phase).astype(int)
+    want_cnt = np.bincount(pbin, minlength=n_phase)
+    want = np.zeros((n_phase, 4))
+    np.add.at(want, pbin, x.astype('f8'))
+    lo = np.array([i_first], dtype=np.int64)
+    hi = np.array([i_first + n], dtype=np.int64)
+    d_in = backend.to_dev(x)
+    d_lo, d_hi = backend.to_dev(lo), backend.to_dev(hi)
+    d_sum = backend.zeros((1, n_phase, 4), 'f4')
+    d_cnt = backend.zeros((1, n_phase), 'i8')
+    backend.lib.check(backend.lib.bbt_fold_exec(
+        backend.ptr(d_in), 0, n, 4, i_first, backend.ptr(d_lo),
+        backend.ptr(d_hi), 0, 1, None,
+        coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(coef),
+        i_ref, rate, n_phase, backend.ptr(d_sum), backend.ptr(d_cnt),
+        backend.stream))
+    backend.sync()
+    np.testing.assert_array_equal(backend.to_host(d_cnt)[0], want_cnt)
+    got = backend.to_host(d_sum)[0]
+    scale = np.sqrt(np.maximum(want_cnt, 1))[:, None]
+    assert np.abs(got - want).max() <= 1e-5 * scale.max() * 4
+
+
 @pytest.mark.parametrize('bps', [1, 2, 4, 8])
 @pytest.mark.parametrize('n', [1, 13, 4096, 100003])
 def test_decode(backend, bps, n):
