@@ -34,6 +34,69 @@ struct alignas(16) cf2 {  // two adjacent series (e.g. both polarizations)
 };
 
 BBT_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+
+// Complex arithmetic.  On sm_100a a complex value sits in an aligned register
+// pair and is worked on by the packed FP32 instructions (FADD2 / FMUL2 /
+// FFMA2: two lanes per instruction, half the issue slots of scalar code);
+// ptxas turns the swapped, broadcast and half-negated operands written out
+// below into operand modifiers (.LO_HI, .F32, .NP), so they cost nothing.
+#ifndef BBT_F32X2
+#define BBT_F32X2 1
+#endif
+#if defined(__CUDA_ARCH__) && BBT_F32X2
+#define BBT_PACKED 1
+typedef unsigned long long u64x;
+BBT_D u64x p2(float x, float y) {
+  u64x r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+BBT_D u64x p2(cf a) { return p2(a.x, a.y); }
+BBT_D cf u2(u64x v) {
+  cf r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+BBT_D u64x add2(u64x a, u64x b) {
+  u64x r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+BBT_D u64x sub2(u64x a, u64x b) {
+  u64x r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+BBT_D u64x mul2(u64x a, u64x b) {
+  u64x r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+BBT_D u64x fma2(u64x a, u64x b, u64x c) {
+  u64x r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+BBT_D cf operator+(cf a, cf b) { return u2(add2(p2(a), p2(b))); }
+BBT_D cf operator-(cf a, cf b) { return u2(sub2(p2(a), p2(b))); }
+BBT_D cf cmul(cf a, cf b) {
+  return u2(fma2(p2(-a.y, a.x), p2(b.y, b.y), mul2(p2(a), p2(b.x, b.x))));
+}
+BBT_D cf cmulc(cf a, cf b) {  // a * conj(b)
+  return u2(fma2(p2(a.y, -a.x), p2(b.y, b.y), mul2(p2(a), p2(b.x, b.x))));
+}
+BBT_D cf cscale(cf a, float s) { return u2(mul2(p2(a), p2(s, s))); }
+// a + (wr, wi) b
+BBT_D cf cfma(cf a, cf b, float wr, float wi) {
+  return u2(fma2(p2(-b.y, b.x), p2(wi, wi), fma2(p2(b), p2(wr, wr), p2(a))));
+}
+// s = a + w b and d = a - w b = 2 a - s for w = (wr, wi).
+BBT_D void fma_pm(cf a, cf b, float wr, float wi, cf& s, cf& d) {
+  const u64x ps = fma2(p2(-b.y, b.x), p2(wi, wi), fma2(p2(b), p2(wr, wr), p2(a)));
+  s = u2(ps);
+  d = u2(fma2(p2(a), p2(2.f, 2.f), p2(-s.x, -s.y)));
+}
+#else
 BBT_HD cf operator+(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
 BBT_HD cf operator-(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
 BBT_HD cf cmul(cf a, cf b) {
@@ -42,8 +105,22 @@ BBT_HD cf cmul(cf a, cf b) {
 BBT_HD cf cmulc(cf a, cf b) {  // a * conj(b)
   return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
-BBT_HD cf cconj(cf a) { return mk(a.x, -a.y); }
 BBT_HD cf cscale(cf a, float s) { return mk(a.x * s, a.y * s); }
+BBT_HD cf cfma(cf a, cf b, float wr, float wi) {
+  return mk(fmaf(wr, b.x, fmaf(-wi, b.y, a.x)), fmaf(wr, b.y, fmaf(wi, b.x, a.y)));
+}
+// s = a + w b and d = a - w b = 2 a - s for a constant w = (wr, wi): six
+// fused multiply-adds instead of a complex multiply and two additions.
+BBT_HD void fma_pm(cf a, cf b, float wr, float wi, cf& s, cf& d) {
+  s.x = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+  s.y = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+  d.x = fmaf(2.f, a.x, -s.x);
+  d.y = fmaf(2.f, a.y, -s.y);
+}
+#endif
+// b * (wr, wi) for a constant w.
+BBT_HD cf cmulk(cf b, float wr, float wi) { return cmul(b, mk(wr, wi)); }
+BBT_HD cf cconj(cf a) { return mk(a.x, -a.y); }
 BBT_HD cf mul_mi(cf a) { return mk(a.y, -a.x); }  // a * (-i)
 BBT_HD cf mul_pi(cf a) { return mk(-a.y, a.x); }  // a * (+i)
 
@@ -90,9 +167,9 @@ struct Dft<8> {
     Dft<4>::run(a);
     Dft<4>::run(b);
     // b[k1] *= W8^{k1}
-    b[1] = mk((b[1].x + b[1].y) * h, (b[1].y - b[1].x) * h);
+    b[1] = cmulk(b[1], h, -h);
     b[2] = mul_mi(b[2]);
-    b[3] = mk((b[3].y - b[3].x) * h, -(b[3].x + b[3].y) * h);
+    b[3] = cmulk(b[3], -h, -h);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       v[k] = a[k] + b[k];
@@ -100,15 +177,6 @@ struct Dft<8> {
     }
   }
 };
-
-// s = a + w b and d = a - w b = 2 a - s for a constant w = (wr, wi): six
-// fused multiply-adds instead of a complex multiply and two additions.
-BBT_HD void fma_pm(cf a, cf b, float wr, float wi, cf& s, cf& d) {
-  s.x = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
-  s.y = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
-  d.x = fmaf(2.f, a.x, -s.x);
-  d.y = fmaf(2.f, a.y, -s.y);
-}
 
 template <>
 struct Dft<16> {
@@ -146,7 +214,7 @@ struct Dft<16> {
     {  // k1 = 2: W16^2, W16^4 = -i, W16^6
       const cf b2 = mul_mi(a[2][2]);
       const cf s02 = a[0][2] + b2, d02 = a[0][2] - b2;
-      const cf b1 = mk((a[1][2].x + a[1][2].y) * h, (a[1][2].y - a[1][2].x) * h);
+      const cf b1 = cmulk(a[1][2], h, -h);
       cf s13, d13;
       fma_pm(b1, a[3][2], -h, -h, s13, d13);
       d13 = mul_mi(d13);
@@ -226,12 +294,7 @@ struct Dft<32> {
       } else {
         // X = e + w o and X' = e - w o = 2 e - X, w = (c, -s), as six fused
         // multiply-adds instead of a complex multiply and two additions.
-        const cf e = ev[k], o = od[k];
-        cf x;
-        x.x = fmaf(c[k], o.x, fmaf(s[k], o.y, e.x));
-        x.y = fmaf(c[k], o.y, fmaf(-s[k], o.x, e.y));
-        v[k] = x;
-        v[k + 16] = mk(fmaf(2.f, e.x, -x.x), fmaf(2.f, e.y, -x.y));
+        fma_pm(ev[k], od[k], c[k], -s[k], v[k], v[k + 16]);
       }
     }
   }

@@ -124,8 +124,8 @@ def sec_dd():
     HC, HR = 4096, 8192   # half-size tiles in column / row passes
     FR = 16384            # full-size row tiles for the interleaved layout
     for (N, S, frames, hints) in (
-            (1 << 20, 16, 4, (0, I | FR, P, I | HC)),
-            (1 << 24, 2, 2, (0, HC, 11 | P | HR)),
+            (1 << 20, 16, 16, (0, I | FR, P, I | HC)),
+            (1 << 24, 2, 8, (0, HC, 11 | P | HR)),
             (1 << 22, 2, 4, (0, HC, 9 | P | HR)),
             (1 << 14, 2050, 2, (0,)),
             (1 << 13, 2050, 4, (0,))):
