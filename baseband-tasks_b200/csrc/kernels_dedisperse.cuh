@@ -295,12 +295,14 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       if (PLANAR) {
         base2 += (long long)nb * C::G * C::N;
       } else {
-        if (a.row_chunks == 1) {
-          base2 += ((long long)nb * a.row_rpc) * C::N * a.S;
-          elems = (long long)a.row_rpc * C::N * a.S;
-        } else {
-          elems = 0;  // strided chunks: leave to the hardware
-        }
+        // The tiles of one row block (its `row_chunks` groups of series) are
+        // interleaved in memory; together they form one contiguous range, of
+        // which each of their CTAs fetches an equal contiguous share, so that
+        // DRAM sees whole lines rather than the 64-byte pieces of one tile.
+        const unsigned chunks = a.row_chunks;
+        const unsigned rb = nb / chunks, ck = nb - rb * chunks;
+        elems = (long long)a.row_rpc * C::N * a.S / chunks;
+        base2 += ((long long)rb * a.row_rpc) * C::N * a.S + ck * elems;
       }
       const long long limit = a.N * a.S - (base2 - (a.work + nf * a.N * a.S));
       if (elems > limit) elems = limit;

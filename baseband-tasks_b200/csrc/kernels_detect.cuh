@@ -118,6 +118,15 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
       INTEGRATE && C::SMEM_BYTES + (size_t)C::G * C::N * sizeof(cf) <= 200 * 1024;
   cf* stage = smem + (C::SMEM_BYTES / sizeof(cf)) + (size_t)t * C::G + g;
   const long long pstep = (long long)C::T * row;
+  // CTAs sharing one spectrum block (when the series divide evenly).
+  long long share = 0, share_at = 0, jsub0 = 0;
+  if (STAGE && a.M % (C::G / 2) == 0) {
+    const long long nshare = a.M / (C::G / 2);
+    jsub0 = blockIdx.x / nshare;
+    share = (long long)C::N * row / nshare;
+    share_at = (blockIdx.x - jsub0 * nshare) * share;
+    if (jsub0 >= a.msub) share = 0;
+  }
   if (STAGE && lo < hi) {
     const long long j = lo + jsub;
     const bool valid = lane_ok && j < hi;
@@ -146,6 +155,15 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
           cp_async8(stage + e * (C::T * C::G), nvalid ? pe : in, nvalid);
           pe += pstep;
         }
+      }
+      if (share > 0 && j0 + 2 * a.msub < hi) {
+        // The spectrum after next, into L2: the CTAs that split the series
+        // of a spectrum each ask for a contiguous share of its block, so
+        // DRAM sees whole lines rather than each CTA's 64-byte pieces.
+        const cf* pb = in + ((j0 + 2 * a.msub + jsub0) * C::N) * row + share_at;
+        for (long long i = (long long)tid * 16; i < share;
+             i += (long long)C::THREADS * 16)
+          prefetch_l2(pb + i);
       }
     } else {
       {
