@@ -450,8 +450,9 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 
 #ifndef BBT_TW_SQUARE
 // 1: powers of two of the twiddle by squaring instead of look-ups; 2: w^8 and
-// w^16 looked up (less rounding error, two more loads); 0: all looked up.
-#define BBT_TW_SQUARE 1
+// w^16 looked up (less rounding error, two more loads; the default, see
+// BBT_RAMP_SQUARE for the measurements); 0: all looked up.
+#define BBT_TW_SQUARE 2
 #endif
 // b[r] *= w^r for r < R, with w = tw[kk]: powers of two are looked up, the
 // others are products of two looked-up or derived values.

@@ -64,6 +64,38 @@ BBT_HD void prefetch_tile(const cf* base, int rows, long long stride,
   }
 }
 
+// The twiddle W_N^{k1 n2} between the column and the row transforms is applied
+// in the column passes (they are bound by memory and have arithmetic to
+// spare; the row pass is bound by arithmetic): a thread holding the elements
+// k1 = t + T e of column n2 multiplies them by scale * W_N^{n2 k1}, generated
+// as base * step^e from two table look-ups.
+#ifndef BBT_RAMP_SQUARE
+// 0: every power of the ramp step comes from the table.  1: powers by
+// squaring (one look-up; each squaring doubles the rounding error of the
+// step).  Measured on a 2^24-point dedispersion frame (tools/accuracy.py), max /
+// RMS error in units of the RMS: 1.2e-5 / 1.3e-6 with squaring here and in
+// apply_twiddles (BBT_TW_SQUARE=1) -- outside the 1e-5 parity tolerance --,
+// 5.9e-6 / 9.6e-7 with 0 here, 2.5e-6 / 4.2e-7 with 0 here and
+// BBT_TW_SQUARE=2 (the defaults; 2-4 % slower than all squaring).  numpy's
+// single-precision path: 8.6e-7 / 1.9e-7.
+#define BBT_RAMP_SQUARE 0
+#endif
+template <class C, int MODE>
+BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
+  cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
+  const cf base = cscale(big.get((long long)k1 * t), scale);
+#if BBT_RAMP_SQUARE
+  pw[0] = big.get((long long)k1 * C::T);
+#pragma unroll
+  for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
+#else
+#pragma unroll
+  for (int b = 0; b < C::LOG2E; ++b)
+    pw[b] = big.get(((long long)k1 * C::T) << b);
+#endif
+  Ramp<C::LOG2E, MODE>::run(v, base, pw);
+}
+
 // Pass 1: forward column FFTs, frame -> work.  Lanes are consecutive flat
 // columns q = n2*S + s.
 template <class C>
@@ -104,10 +136,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
+    const unsigned n2 = (unsigned)col / (unsigned)a.S;
+    row_ramp<C, 0>(v, a.big, (int)n2, t, 1.f);
     cf* dst = a.work + frame * a.N * a.S;
     long long step;
     if (a.planar) {
-      const unsigned n2 = (unsigned)col / (unsigned)a.S;
       const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
       const long long N2 = a.N >> a.log2n1;
       dst += s * N2 + n2;
@@ -155,7 +188,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     const long long pstep = (long long)C::T * step;
 #pragma unroll
     for (int e = 0; e < C::E; ++e) {
-      v[e] = valid ? cconj(ld_stream(pe)) : mk(0.f, 0.f);
+      v[e] = valid ? ld_stream(pe) : mk(0.f, 0.f);
       pe += pstep;
     }
   }
@@ -185,6 +218,9 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       }
     }
   }
+  // The row pass left fft(conj(Y)) = conj(ifft(Y)) N; times the twiddle and
+  // 1/N this is the conjugate of what the inverse column transform takes.
+  if (valid) row_ramp<C, 0>(v, a.big, (int)((unsigned)col / (unsigned)a.S), t, a.scale);
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
@@ -198,35 +234,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       dst += fstep;
     }
   }
-}
-
-// Multiply the elements n2 = t + T e of row k1 by the twiddle W_N^{k1 n2}
-// (MODE 0) or by its conjugate and the scale (MODE 1: v <- conj(v w) scale),
-// generated as base * step^e from two table look-ups.  Called before and
-// after the transforms rather than keeping the powers in registers.
-#ifndef BBT_RAMP_SQUARE
-// 1: powers of the ramp step by squaring (fastest; each squaring doubles the
-// rounding error of the step).  0: every power from the table.  Measured on
-// a 2^24-point dedispersion (tools/accuracy.py): RMS error 1.3e-6 of the RMS
-// with squaring here and in apply_twiddles, 4.3e-7 with BBT_RAMP_SQUARE=0 and
-// BBT_TW_SQUARE=2 at 3 % less throughput (numpy's single-precision path:
-// 1.9e-7; the parity tolerance is 1e-5).
-#define BBT_RAMP_SQUARE 1
-#endif
-template <class C, int MODE>
-BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
-  cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
-  const cf base = cscale(big.get((long long)k1 * t), scale);
-#if BBT_RAMP_SQUARE
-  pw[0] = big.get((long long)k1 * C::T);
-#pragma unroll
-  for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
-#else
-#pragma unroll
-  for (int b = 0; b < C::LOG2E; ++b)
-    pw[b] = big.get(((long long)k1 * C::T) << b);
-#endif
-  Ramp<C::LOG2E, MODE>::run(v, base, pw);
 }
 
 // Pass 2 on one row per lane.  PLANAR: lanes are G consecutive rows
@@ -311,7 +318,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
         prefetch_l2(base2 + i);
     }
   }
-  if (valid) row_ramp<C, 0>(v, a.big, (int)k1, t, 1.f);
   if (PLANAR) {
     SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
     block_fft<C>(v, t, a.tw, sm);
@@ -333,8 +339,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     block_fft<C>(v, t, a.tw, sm);
   }
   if (valid) {
-    // conj(fft(conj(Y))) * conj(w) / N = conj(fft(conj(Y)) * w) / N
-    row_ramp<C, 1>(v, a.big, (int)k1, t, a.scale);
+    // fft(conj(Y)); the inverse column pass applies the twiddle and 1/N.
 #pragma unroll
     for (int e = 0; e < C::E; ++e)
       row[off0 + (unsigned)(C::T * e) * ustride] = v[e];
