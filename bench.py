@@ -568,7 +568,7 @@ def run_reference(args):
         'impl': 'reference',
         'metric': 'Dedisperse->Channelize->Power->Integrate complex '
                   'Gsamples/s',
-        'value': value, 'unit': 'Gsamples/s', 'n_gpus': 0,
+        'value': value, 'unit': 'Gsamples/s', 'n_gpus': int(args.gpus),
         'steps': steps, 'warmup': min(args.warmup, 1),
         'ms_per_step': wall / steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64 (fp32)',
