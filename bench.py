@@ -453,9 +453,9 @@ def run_b200(args):
         'roofline': roofline,
         'chain_roofline': {
             'model_bytes_per_sample': mb,
-            'achieved_gbs': value * mb, 'peak': peak,
-            'frac': value * mb / peak, 'frac_of_8TBs_nominal':
-            value * mb / 8000.},
+            'achieved_gbs': value * mb, 'peak': peak * world,
+            'frac': value * mb / (peak * world), 'frac_of_8TBs_nominal':
+            value * mb / (8000. * world)},
         'kernels': shares,
         'cpu_baseline': cpu,
     }
