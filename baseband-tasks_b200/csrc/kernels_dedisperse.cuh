@@ -72,7 +72,7 @@ BBT_HD void prefetch_tile(const cf* base, int rows, long long stride,
 #ifndef BBT_RAMP_SQUARE
 // 0: every power of the ramp step comes from the table.  1: powers by
 // squaring (one look-up; each squaring doubles the rounding error of the
-// step).  Measured on a 2^24-point dedispersion frame (tools/accuracy.py), max /
+// step).  Measured on a 2^24-point dedispersion frame (tests/accuracy.py), max /
 // RMS error in units of the RMS: 1.2e-5 / 1.3e-6 with squaring here and in
 // apply_twiddles (BBT_TW_SQUARE=1) -- outside the 1e-5 parity tolerance --,
 // 5.9e-6 / 9.6e-7 with 0 here, 2.5e-6 / 4.2e-7 with 0 here and

@@ -1,6 +1,6 @@
 """Numerical accuracy of the GPU FFT and dedispersion against float64 (GPU only).
 
-Usage: [BBT_B200_LIB=...] python tools/accuracy.py
+Usage: [BBT_B200_LIB=...] python tests/accuracy.py
 Prints max and RMS errors relative to the RMS of the float64 result, next to
 the same figures for numpy's single-precision FFT.
 """
