@@ -168,6 +168,14 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
   return check_launch("integrate kernel");
 }
 
+// 1: feed the fold kernel from TMA-staged tiles (cp.async.bulk + mbarrier rings
+// per warp).  Parity-tested on the B200 and measured slower than direct
+// streaming loads (0.52 against 0.34 ms per C5 launch: every sample is used
+// once, so the detour through shared memory only adds latency and costs a
+// fourth resident CTA), hence off.
+#ifndef BBT_FOLD_TMA
+#define BBT_FOLD_TMA 0
+#endif
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
                   int64_t i_first, const int64_t* lo, const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,
@@ -206,18 +214,32 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
   a.n_phase = n_phase;
   const size_t smem = (size_t)n_phase * (inner + 1) * 4;
   a.use_smem = smem <= 40 * 1024;
-  if (a.use_smem && inner == 4 && !(reinterpret_cast<uintptr_t>(in) & 15))
+  size_t smem_total = a.use_smem ? smem : 0;
+  if (a.use_smem && inner == 4 && !(reinterpret_cast<uintptr_t>(in) & 15)) {
     a.use_smem = 2;
+#if !defined(BBT_EMULATE) && BBT_FOLD_TMA
+    if (!pbin) {
+      // A ring of kFoldStages tiles filled by bulk copies, plus its barriers.
+      a.use_smem = 3;
+      a.ring_offset = (int)((smem + 127) / 128 * 128);
+      smem_total = a.ring_offset + (size_t)kFoldStages * kFoldTile * 16 +
+                   kFoldStages * (kFoldThreads / 32) * 8;
+    }
+#endif
+  }
   const int64_t chunks = std::max<int64_t>(
       1, std::min<int64_t>(ceil_div((int64_t)sm_count() * 8, n_bins),
                            ceil_div(n, n_bins * 1024)));
   dim3 grid((unsigned)chunks, (unsigned)n_bins);
   prof_next_name = "fold";
+  if (BBT_SET_SMEM(fold_kernel<true>, smem_total) ||
+      BBT_SET_SMEM(fold_kernel<false>, smem_total))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
   if (power)
-    BBT_LAUNCH(fold_kernel<true>, grid, dim3(kFoldThreads), a.use_smem ? smem : 0,
+    BBT_LAUNCH(fold_kernel<true>, grid, dim3(kFoldThreads), smem_total,
                as_stream(stream), a);
   else
-    BBT_LAUNCH(fold_kernel<false>, grid, dim3(kFoldThreads), a.use_smem ? smem : 0,
+    BBT_LAUNCH(fold_kernel<false>, grid, dim3(kFoldThreads), smem_total,
                as_stream(stream), a);
   return check_launch("fold kernel");
 }

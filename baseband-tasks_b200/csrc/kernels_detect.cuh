@@ -282,7 +282,9 @@ struct FoldArgs {
   int ncoef;
   int n_phase;
   int use_smem;               // privatise the profile in shared memory
-                              // (2: and take the four-values-per-sample path)
+                              // (2: and take the four-values-per-sample path;
+                              //  3: with TMA-staged tiles)
+  int ring_offset;            // bytes from the profile to the tile ring
 };
 
 BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
@@ -303,6 +305,8 @@ BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
 constexpr int kFoldFast = 8;  // most values per sample kept in registers
 constexpr int kFoldUnroll = 4;  // samples in flight per thread (4 values each)
 constexpr int kFoldThreads = 256;
+constexpr int kFoldStages = 4;  // tiles in flight in the TMA-staged variant
+constexpr int kFoldTile = kFoldThreads * kFoldUnroll;  // samples per tile
 
 #if defined(__CUDA_ARCH__)
 // Phase bin of absolute sample index xi (already a double; exact below 2^53),
@@ -345,15 +349,17 @@ BBT_DEV int fold_phase_bin_fast(const FoldArgs& a, const FoldPhase& f, double xi
 // 128 values with six shuffles (lanes trade halves, then quarters, of their
 // values before the plain butterfly), leaving component c in the lanes with
 // (lane >> 3) == c, where it is kept in a running sum until the bin changes.
+template <bool POWER, bool CHECK, int USTRIDE>
+BBT_DEV void fold_four_bins(const FoldArgs& a, const FoldPhase& f, float* hist,
+                            unsigned* hcnt, const f4* x, long long ib,
+                            long long i1, double xd, int lane, float& acc,
+                            unsigned& acc_n, int& cur);
+
 template <bool POWER, bool CHECK>
 BBT_DEV void fold_four_tile(const FoldArgs& a, const FoldPhase& f, float* hist,
                             unsigned* hcnt, long long ib, long long i1, double xd,
                             int lane, float& acc, unsigned& acc_n, int& cur) {
-  const unsigned full = 0xffffffffu;
-  const int comp = lane >> 3;
-  const bool flusher = (lane & 7) == 0;
   f4 x[kFoldUnroll];
-  int p[kFoldUnroll];
 #pragma unroll
   for (int u = 0; u < kFoldUnroll; ++u) {
     const long long i = ib + u * kFoldThreads + lane;
@@ -363,9 +369,23 @@ BBT_DEV void fold_four_tile(const FoldArgs& a, const FoldPhase& f, float* hist,
       x[u].x = q.x, x[u].y = q.y, x[u].z = q.z, x[u].w = q.w;
     }
   }
+  fold_four_bins<POWER, CHECK, kFoldThreads>(a, f, hist, hcnt, x, ib, i1, xd,
+                                             lane, acc, acc_n, cur);
+}
+
+// x[u] is the sample ib + u * USTRIDE + lane.
+template <bool POWER, bool CHECK, int USTRIDE>
+BBT_DEV void fold_four_bins(const FoldArgs& a, const FoldPhase& f, float* hist,
+                            unsigned* hcnt, const f4* x, long long ib,
+                            long long i1, double xd, int lane, float& acc,
+                            unsigned& acc_n, int& cur) {
+  const unsigned full = 0xffffffffu;
+  const int comp = lane >> 3;
+  const bool flusher = (lane & 7) == 0;
+  int p[kFoldUnroll];
 #pragma unroll
   for (int u = 0; u < kFoldUnroll; ++u) {
-    const long long i = ib + u * kFoldThreads + lane;
+    const long long i = ib + u * USTRIDE + lane;
     p[u] = -1;
     if (!CHECK || i < i1) {
       if (a.pbin) {
@@ -373,13 +393,13 @@ BBT_DEV void fold_four_tile(const FoldArgs& a, const FoldPhase& f, float* hist,
         q = q < 0 ? 0 : q;
         p[u] = q >= a.n_phase ? a.n_phase - 1 : q;
       } else {
-        p[u] = fold_phase_bin_fast(a, f, xd + (double)(u * kFoldThreads));
+        p[u] = fold_phase_bin_fast(a, f, xd + (double)(u * USTRIDE));
       }
     }
   }
 #pragma unroll
   for (int u = 0; u < kFoldUnroll; ++u) {
-    if (CHECK && ib + u * kFoldThreads >= i1) break;  // warp-uniform
+    if (CHECK && ib + u * USTRIDE >= i1) break;  // warp-uniform
     f4 v = x[u];
     if (POWER) {
       cf xa, xb;
@@ -443,6 +463,106 @@ BBT_DEV void fold_four(const FoldArgs& a, float* hist, unsigned* hcnt,
     if (lane == 0) atomicAdd(hcnt + cur, acc_n);
   }
 }
+
+// The same with TMA-staged tiles: lane 0 of every warp keeps kFoldStages bulk
+// copies (cp.async.bulk, 2 KB = 128 samples each, completion counted on an
+// mbarrier) in flight into the warp's own ring in shared memory, so the loads
+// in flight are bounded neither by registers nor by the other warps; the
+// warps of a CTA take consecutive 128-sample pieces in turn.
+BBT_DEV unsigned smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+BBT_DEV void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  for (unsigned spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spins > (1u << 28)) __trap();  // a lost copy must not hang the GPU
+  }
+}
+
+template <bool POWER>
+BBT_DEV void fold_four_staged(const FoldArgs& a, float* hist, unsigned* hcnt,
+                              long long i0, long long i1, float4* ring,
+                              unsigned long long* bars) {
+  constexpr int WT = 32 * kFoldUnroll;           // samples per warp tile
+  constexpr int NW = kFoldThreads / 32;          // warps per CTA
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  FoldPhase f;
+  f.i_ref = a.i_ref, f.rate = a.rate, f.inv_rate = a.inv_rate;
+  f.c0 = a.coef[0], f.c1 = a.coef[1], f.c2 = a.coef[2], f.c3 = a.coef[3];
+  f.n_phase = (double)a.n_phase;
+  const long long n = i1 - i0;
+  const long long nt = (n + WT - 1) / WT;        // warp tiles in this chunk
+  const float4* src = static_cast<const float4*>(a.in) + i0;
+  float4* wring = ring + (size_t)w * kFoldStages * WT;
+  unsigned long long* wbars = bars + w * kFoldStages;
+  if (lane == 0) {
+    for (int s = 0; s < kFoldStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(
+          smem_addr(wbars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](long long kt, int s) {  // lane 0: start the copy of tile kt
+    const long long first = kt * WT;
+    const long long left = n - first;
+    const unsigned bytes = (unsigned)(left < WT ? left : WT) * 16u;
+    const unsigned bar = smem_addr(wbars + s);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1], %2, [%3];" ::"r"(smem_addr(wring + (size_t)s * WT)),
+        "l"(src + first), "r"(bytes), "r"(bar)
+        : "memory");
+  };
+  if (lane == 0)
+    for (int s = 0; s < kFoldStages; ++s)
+      if (w + (long long)s * NW < nt) issue(w + (long long)s * NW, s);
+  float acc = 0.f;
+  unsigned acc_n = 0;
+  int cur = -1;
+  int j = 0;
+  for (long long kt = w; kt < nt; kt += NW, ++j) {
+    const int s = j % kFoldStages;
+    mbar_wait(smem_addr(wbars + s), (unsigned)(j / kFoldStages) & 1u);
+    const float4* tile = wring + (size_t)s * WT;
+    const long long first = i0 + kt * WT;
+    const bool whole = first + WT <= i1;
+    f4 x[kFoldUnroll];
+#pragma unroll
+    for (int u = 0; u < kFoldUnroll; ++u) {
+      const int idx = u * 32 + lane;
+      x[u].x = x[u].y = x[u].z = x[u].w = 0.f;
+      if (whole || first + idx < i1) {
+        const float4 q = tile[idx];
+        x[u].x = q.x, x[u].y = q.y, x[u].z = q.z, x[u].w = q.w;
+      }
+    }
+    __syncwarp();  // the warp has taken its samples: the stage is free
+    const long long knext = kt + (long long)kFoldStages * NW;
+    if (lane == 0 && knext < nt) issue(knext, s);
+    const double xd = (double)(a.i_first + first + lane);
+    if (whole)
+      fold_four_bins<POWER, false, 32>(a, f, hist, hcnt, x, first, i1, xd, lane,
+                                       acc, acc_n, cur);
+    else
+      fold_four_bins<POWER, true, 32>(a, f, hist, hcnt, x, first, i1, xd, lane,
+                                      acc, acc_n, cur);
+  }
+  if (cur >= 0 && (lane & 7) == 0) {
+    atomicAdd(hist + cur * 4 + (lane >> 3), acc);
+    if (lane == 0) atomicAdd(hcnt + cur, acc_n);
+  }
+}
 #endif
 
 template <bool POWER>
@@ -467,8 +587,17 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
   unsigned long long* gcnt = a.count + b * a.n_phase;
   const long long width = POWER ? a.inner / 4 : a.inner;  // input items per sample
 #if defined(__CUDA_ARCH__)
-  if (a.use_smem == 2) {
-    fold_four<POWER>(a, hist, hcnt, i0, i1);
+  if (a.use_smem >= 2) {
+    if (a.use_smem == 3) {
+      // Ring and barriers follow the profile (16-byte aligned by the launcher).
+      char* base = reinterpret_cast<char*>(hist) + a.ring_offset;
+      fold_four_staged<POWER>(
+          a, hist, hcnt, i0, i1, reinterpret_cast<float4*>(base),
+          reinterpret_cast<unsigned long long*>(
+              base + (size_t)kFoldStages * kFoldTile * 16));  // after the rings
+    } else {
+      fold_four<POWER>(a, hist, hcnt, i0, i1);
+    }
   } else if (a.use_smem && a.inner <= kFoldFast) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
