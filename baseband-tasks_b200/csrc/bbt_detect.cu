@@ -168,14 +168,6 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
   return check_launch("integrate kernel");
 }
 
-// 1: feed the fold kernel from TMA-staged tiles (cp.async.bulk + mbarrier rings
-// per warp).  Parity-tested on the B200 and measured slower than direct
-// streaming loads (0.52 against 0.34 ms per C5 launch: every sample is used
-// once, so the detour through shared memory only adds latency and costs a
-// fourth resident CTA), hence off.
-#ifndef BBT_FOLD_TMA
-#define BBT_FOLD_TMA 0
-#endif
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
                   int64_t i_first, const int64_t* lo, const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,

@@ -302,10 +302,21 @@ BBT_DEV int fold_phase_bin(const FoldArgs& a, long long i_abs) {
 // if so it reduces them with shuffles and lane 0 adds the total to a running
 // per-warp accumulator that is only flushed (one atomic per value) when the
 // bin changes.  Mixed warps fall back to one shared-memory atomic per sample.
+// 1: feed the fold kernel from TMA-staged tiles (cp.async.bulk + mbarrier rings
+// per warp).  Parity-tested on the B200 and measured slower than direct
+// streaming loads (0.52 against 0.34 ms per C5 launch: every sample is used
+// once, so the detour through shared memory only adds latency and costs a
+// fourth resident CTA), hence off.
+#ifndef BBT_FOLD_TMA
+#define BBT_FOLD_TMA 0
+#endif
 constexpr int kFoldFast = 8;  // most values per sample kept in registers
 constexpr int kFoldUnroll = 4;  // samples in flight per thread (4 values each)
 constexpr int kFoldThreads = 256;
-constexpr int kFoldStages = 4;  // tiles in flight in the TMA-staged variant
+#ifndef BBT_FOLD_STAGES
+#define BBT_FOLD_STAGES 4
+#endif
+constexpr int kFoldStages = BBT_FOLD_STAGES;  // tiles in flight in the TMA-staged variant
 constexpr int kFoldTile = kFoldThreads * kFoldUnroll;  // samples per tile
 
 #if defined(__CUDA_ARCH__)
@@ -464,6 +475,7 @@ BBT_DEV void fold_four(const FoldArgs& a, float* hist, unsigned* hcnt,
   }
 }
 
+#if BBT_FOLD_TMA
 // The same with TMA-staged tiles: lane 0 of every warp keeps kFoldStages bulk
 // copies (cp.async.bulk, 2 KB = 128 samples each, completion counted on an
 // mbarrier) in flight into the warp's own ring in shared memory, so the loads
@@ -563,10 +575,11 @@ BBT_DEV void fold_four_staged(const FoldArgs& a, float* hist, unsigned* hcnt,
     if (lane == 0) atomicAdd(hcnt + cur, acc_n);
   }
 }
+#endif  // BBT_FOLD_TMA
 #endif
 
 template <bool POWER>
-BBT_GLOBAL void fold_kernel(FoldArgs a) {
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(kFoldThreads, 4) fold_kernel(FoldArgs a) {
   float* hist = BBT_SMEM(float);
   unsigned* hcnt = reinterpret_cast<unsigned*>(hist + (size_t)a.n_phase * a.inner);
   const long long b = a.b_first + blockIdx.y;
@@ -588,6 +601,7 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
   const long long width = POWER ? a.inner / 4 : a.inner;  // input items per sample
 #if defined(__CUDA_ARCH__)
   if (a.use_smem >= 2) {
+#if BBT_FOLD_TMA
     if (a.use_smem == 3) {
       // Ring and barriers follow the profile (16-byte aligned by the launcher).
       char* base = reinterpret_cast<char*>(hist) + a.ring_offset;
@@ -595,7 +609,9 @@ BBT_GLOBAL void fold_kernel(FoldArgs a) {
           a, hist, hcnt, i0, i1, reinterpret_cast<float4*>(base),
           reinterpret_cast<unsigned long long*>(
               base + (size_t)kFoldStages * kFoldTile * 16));  // after the rings
-    } else {
+    } else
+#endif
+    {
       fold_four<POWER>(a, hist, hcnt, i0, i1);
     }
   } else if (a.use_smem && a.inner <= kFoldFast) {
