@@ -68,7 +68,7 @@ BBT_HD void prefetch_tile(const cf* base, int rows, long long stride,
 // in the column passes (they are bound by memory and have arithmetic to
 // spare; the row pass is bound by arithmetic): a thread holding the elements
 // k1 = t + T e of column n2 multiplies them by scale * W_N^{n2 k1}, generated
-// as base * step^e from two table look-ups.
+// as base * step^e from a few table look-ups.
 #ifndef BBT_RAMP_SQUARE
 // 0: every power of the ramp step comes from the table.  1: powers by
 // squaring (one look-up; each squaring doubles the rounding error of the
@@ -81,17 +81,17 @@ BBT_HD void prefetch_tile(const cf* base, int rows, long long stride,
 #define BBT_RAMP_SQUARE 0
 #endif
 template <class C, int MODE>
-BBT_HD void row_ramp(cf* v, const BigTwiddle& big, int k1, int t, float scale) {
+BBT_HD void col_twiddle(cf* v, const BigTwiddle& big, int n2, int t, float scale) {
   cf pw[C::LOG2E > 0 ? C::LOG2E : 1];
-  const cf base = cscale(big.get((long long)k1 * t), scale);
+  const cf base = cscale(big.get((long long)n2 * t), scale);
 #if BBT_RAMP_SQUARE
-  pw[0] = big.get((long long)k1 * C::T);
+  pw[0] = big.get((long long)n2 * C::T);
 #pragma unroll
   for (int b = 1; b < C::LOG2E; ++b) pw[b] = cmul(pw[b - 1], pw[b - 1]);
 #else
 #pragma unroll
   for (int b = 0; b < C::LOG2E; ++b)
-    pw[b] = big.get(((long long)k1 * C::T) << b);
+    pw[b] = big.get(((long long)n2 * C::T) << b);
 #endif
   Ramp<C::LOG2E, MODE>::run(v, base, pw);
 }
@@ -137,7 +137,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
     const unsigned n2 = (unsigned)col / (unsigned)a.S;
-    row_ramp<C, 0>(v, a.big, (int)n2, t, 1.f);
+    col_twiddle<C, 0>(v, a.big, (int)n2, t, 1.f);
     cf* dst = a.work + frame * a.N * a.S;
     long long step;
     if (a.planar) {
@@ -220,7 +220,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   }
   // The row pass left fft(conj(Y)) = conj(ifft(Y)) N; times the twiddle and
   // 1/N this is the conjugate of what the inverse column transform takes.
-  if (valid) row_ramp<C, 0>(v, a.big, (int)((unsigned)col / (unsigned)a.S), t, a.scale);
+  if (valid) col_twiddle<C, 0>(v, a.big, (int)((unsigned)col / (unsigned)a.S), t, a.scale);
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   block_fft<C>(v, t, a.tw1, sm);
   if (valid) {
