@@ -94,49 +94,62 @@ def model_bytes(w):
     return 48. / eff + 8. + 8. / per_bin
 
 
-def clocks_sampler(device_index):
-    cmd = ['nvidia-smi', '-i', str(device_index),
-           '--query-gpu=clocks.sm,clocks.max.sm,'
-           'clocks_event_reasons.hw_slowdown,'
-           'clocks_event_reasons.hw_thermal_slowdown,'
-           'clocks_event_reasons.sw_thermal_slowdown,'
-           'clocks_event_reasons.sw_power_cap',
-           '--format=csv,noheader,nounits', '-lms', '100']
-    try:
-        return subprocess.Popen(cmd, stdout=subprocess.PIPE,
-                                stderr=subprocess.DEVNULL, text=True)
-    except OSError:
-        return None
+class ClocksSampler:
+    """nvidia-smi polled every 100 ms in the background; every line is kept
+    with the time it arrived, so the samples taken under load can be picked."""
 
-
-def clocks_summary(proc):
-    if proc is None:
-        return None
-    proc.terminate()
-    try:
-        out, _ = proc.communicate(timeout=5)
-    except Exception:
-        proc.kill()
-        return None
-    sm, smax, reasons = [], 0., set()
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
-    for line in out.strip().splitlines():
-        parts = [p.strip() for p in line.split(',')]
-        if len(parts) < 6:
-            continue
+    def __init__(self, device_index):
+        import threading
+        cmd = ['nvidia-smi', '-i', str(device_index),
+               '--query-gpu=clocks.sm,clocks.max.sm,'
+               'clocks_event_reasons.hw_slowdown,'
+               'clocks_event_reasons.hw_thermal_slowdown,'
+               'clocks_event_reasons.sw_thermal_slowdown,'
+               'clocks_event_reasons.sw_power_cap',
+               '--format=csv,noheader,nounits', '-lms', '100']
+        self.samples = []
         try:
-            sm.append(float(parts[0]))
-            smax = max(smax, float(parts[1]))
-        except ValueError:
-            continue
-        for name, val in zip(names, parts[2:6]):
-            if val.lower().startswith('active'):
-                reasons.add(name)
-    if not sm:
-        return None
-    return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': smax,
-            'reasons': sorted(reasons), 'samples': len(sm)}
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.monotonic(), line))
+
+    def count(self, t0):
+        return sum(1 for t, _ in self.samples if t >= t0)
+
+    def summary(self, t0, t1):
+        """Median SM clock and throttle reasons of the samples in [t0, t1]."""
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, smax, reasons = [], 0., set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for t, line in list(self.samples):
+            if not t0 <= t <= t1:
+                continue
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = max(smax, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': smax,
+                'reasons': sorted(reasons), 'samples': len(sm)}
 
 
 # --------------------------------------------------------------- GPU arm
@@ -339,14 +352,27 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
+    sampler = ClocksSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         res = step_resident()
     out_bytes = res.numel() * res.element_size()
-    sampler = clocks_sampler(local) if rank == 0 else None
     l0 = lib.bbt_launch_count()
+    t_load = time.monotonic()
     ms = timed(step_resident, args.steps)
     launches = lib.bbt_launch_count() - l0
-    clocks = clocks_summary(sampler)
+    # The timed region lasts tens of milliseconds, less than one nvidia-smi
+    # poll: every rank keeps the same load on (untimed) for another ~0.5 s so
+    # that the clocks are sampled under it.
+    n_extra = int(min(5000, np.ceil(500. / max(ms / args.steps, 1e-3))))
+    for _ in range(n_extra):
+        step_resident()
+    barrier()
+    clocks = None
+    if sampler is not None:
+        clocks = sampler.summary(t_load + 0.05, time.monotonic())
+        if clocks is not None:
+            clocks['window'] = ('timed steps plus %d more identical steps'
+                                % n_extra)
 
     for _ in range(2):
         res_e2e = step_e2e()
