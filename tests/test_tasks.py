@@ -330,6 +330,31 @@ def test_dechannelize_roundtrip(bt):
     np.testing.assert_array_equal(dc.frequency, src.frequency)
 
 
+def test_channelize_real_stream(bt):
+    """Real-valued streams (rfft/irfft, fourier/numpy.py:41-49): n//2+1
+    channels; Dechannelize needs the explicit n and the real dtype
+    (channelize.py:128-166)."""
+    rng = np.random.default_rng(21)
+    n = 128
+    x = rng.normal(size=(n * 20, 3)).astype('f4')
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=n,
+                         frequency=400e6, sideband=1)
+    ch = bt.Channelize(src, n, samples_per_frame=5)
+    assert ch.shape == (20, n // 2 + 1, 3) and ch.dtype == np.complex64
+    want = orc.channelize(x, n)
+    assert_voltage(ch.read(), want.astype('c8'))
+    np.testing.assert_allclose(
+        np.asarray(ch.frequency).reshape(-1)[:n // 2 + 1],
+        400e6 + np.fft.rfftfreq(n, 1e-6))
+    with pytest.raises(ValueError):
+        bt.Dechannelize(ch, dtype='f4')        # n is needed for real data
+    dc = bt.Dechannelize(ch, n, dtype='f4')
+    assert dc.shape == x.shape and dc.dtype == np.float32
+    assert dc.sample_rate == src.sample_rate
+    assert_voltage(dc.read(), x)
+    assert dc.read(0).shape == (0, 3)
+
+
 # ---------------------------------------------------------------- integrate
 def fake_pulsar(bt, dtype='f4'):
     """tests/test_integration.py:17-43: 16000x2 @10 kHz, a pulse every 125."""
