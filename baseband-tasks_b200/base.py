@@ -275,9 +275,12 @@ class Base:
         count = self._check_read(count, out)
         data = self._read_data(count)
         if out is None:
+            # The caller gets an array of the stream's dtype (the reference
+            # fills one allocated with it, base.py:425-438).
             if B.is_tensor(data):
-                return data.cpu().numpy()
-            return np.array(data, copy=True)
+                data = data.cpu().numpy()
+                return data.astype(self.dtype, copy=False)
+            return np.array(data, dtype=self.dtype, copy=True)
         out[...] = B.as_host(data)
         return out
 
@@ -288,7 +291,10 @@ class Base:
         next read of this stream and do not modify it.
         """
         count = self._check_read(count, None)
-        return B.as_device(self._read_data(count))
+        data = B.as_device(self._read_data(count))
+        if data.dtype != B.torch_dtype(self.dtype):
+            data = data.to(B.torch_dtype(self.dtype))
+        return data
 
     def _check_read(self, count, out):
         if self.closed:
