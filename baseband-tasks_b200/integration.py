@@ -473,9 +473,6 @@ class Fold(Integrate):
             i_ref = poly.i_ref(ih.start_time, ih.sample_rate)
             coef = poly.coef
             coef_p = coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-        # Time of the first sample folded in this frame (integration.py:375).
-        ih.seek(start)
-        raw_time = ih.time
         pos = start
         while pos < stop:
             nxt = min(stop, (pos // chunk + 1) * chunk)
@@ -488,8 +485,13 @@ class Fold(Integrate):
             if self._fused is None:
                 x = _as_float32(x, src.dtype)
             if poly is None:
-                raw_items = np.arange(pos - start, nxt - start)
-                phases = self.phase(raw_time + raw_items / ih.sample_rate)
+                # Times from the absolute sample index (the reference adds
+                # offsets within the frame to the frame's start time,
+                # integration.py:375-388): the phase bin of a sample then
+                # does not depend on where frames or `start` happen to fall.
+                raw_items = np.arange(pos, nxt)
+                phases = self.phase(ih.start_time
+                                    + raw_items / ih.sample_rate)
                 phases = np.asarray(_cycles(phases), dtype=np.float64)
                 pbin = ((phases % 1.) * self.n_phase).astype(np.int32)
                 d_pbin = B.as_device(pbin)

@@ -1,0 +1,156 @@
+"""Integrate/Fold API semantics after the reference's
+tests/test_integration.py:60-330 (same fake pulsar: 16000 x 2 samples at
+10 kHz, a pulse every 125 samples)."""
+import numpy as np
+import pytest
+
+from test_tasks import bt, start_time, fake_pulsar  # noqa: F401  (fixture)
+
+
+def test_integrate_all_and_part(bt):
+    data, src = fake_pulsar(bt)
+    power = data ** 2
+    st = bt.Square(src)
+    ip = bt.Integrate(st)                        # everything
+    assert ip.shape == (1, 2)
+    assert ip.start_time == src.start_time
+    out = ip.read()
+    np.testing.assert_allclose(out, power.mean(0, keepdims=True), rtol=1e-5)
+    # not averaged: structured samples with data and count
+    ip = bt.Integrate(st, average=False)
+    res = ip.read()
+    assert res.dtype.names == ('data', 'count')
+    assert res['data'].dtype == st.dtype and res['data'].shape == (1, 2)
+    np.testing.assert_allclose(res['data'], power.sum(0, keepdims=True),
+                               rtol=1e-5)
+    assert np.all(res['count'] == 16000)
+    assert 'average=False' in repr(ip)
+    # a part, from a start offset to the end
+    ip = bt.Integrate(st, start=1000, average=False)
+    assert abs((ip.start_time - src.start_time) - 0.1) < 1e-9
+    res = ip.read()
+    np.testing.assert_allclose(res['data'], power[1000:].sum(0, keepdims=True),
+                               rtol=1e-5)
+    assert np.all(res['count'] == 15000)
+
+
+@pytest.mark.parametrize('n', [1, 3])
+@pytest.mark.parametrize('spf', [1, 4, 10])
+def test_integrate_n(bt, n, spf):
+    data, src = fake_pulsar(bt)
+    power = data ** 2
+    st = bt.Square(src)
+    n_sample = 16000 // n
+    ip = bt.Integrate(st, n, average=False, samples_per_frame=spf)
+    assert ip.shape[0] == n_sample
+    assert ip.sample_rate == src.sample_rate / n
+    assert f'step={n}' in repr(ip)
+    for seek in (121, n_sample - 10):
+        ip.seek(seek)
+        assert abs((ip.time - src.start_time) - seek * n / 1e4) < 1e-9
+        res = ip.read(10)
+        assert ip.tell() == seek + 10
+        want = power[seek * n:(seek + 10) * n].reshape(-1, n, 2).sum(1)
+        np.testing.assert_allclose(res['data'], want, rtol=1e-5)
+        assert np.all(res['count'] == n)
+    # the same through a time step, a start offset and a start time
+    want = power[151 * n:161 * n].reshape(-1, n, 2).sum(1)
+    ip = bt.Integrate(st, n / 1e4, average=False, samples_per_frame=spf)
+    assert ip.sample_rate == src.sample_rate / n
+    ip.seek(151)
+    np.testing.assert_allclose(ip.read(10)['data'], want, rtol=1e-5)
+    ip = bt.Integrate(st, n / 1e4, start=151 * n, average=False,
+                      samples_per_frame=spf)
+    assert abs((ip.start_time - src.start_time) - 151 * n / 1e4) < 1e-9
+    np.testing.assert_allclose(ip.read(10)['data'], want, rtol=1e-5)
+    st.seek(151 * n)
+    ip = bt.Integrate(st, n / 1e4, start=st.time, average=False,
+                      samples_per_frame=spf)
+    res = ip.read(10)
+    assert ip.tell() == 10
+    np.testing.assert_allclose(res['data'], want, rtol=1e-5)
+    assert np.all(res['count'] == n)
+
+
+@pytest.mark.parametrize('spf', [1, 4, 10])
+def test_integrate_non_integer_ratio(bt, spf):
+    """2.26 samples per bin: counts 2, 3, 2, 2, 2, 3, 2, 2."""
+    data, src = fake_pulsar(bt)
+    power = data ** 2
+    expected = [2, 3, 2, 2, 2, 3, 2, 2]
+    step = 2.26 / 1e4
+    st = bt.Square(src)
+    ip = bt.Integrate(st, step, average=False, samples_per_frame=spf)
+    assert abs(ip.sample_rate - 1. / step) < 1e-6
+    res = ip.read(8)
+    want = np.add.reduceat(power[:18],
+                           np.add.accumulate([0] + expected[:-1]))
+    np.testing.assert_allclose(res['data'], want, rtol=1e-5)
+    assert np.all(res['count'].reshape(8, -1).T == expected)
+    for k, m in ((1, 7), (3, 5)):
+        t = src.start_time + k * step
+        ip2 = bt.Integrate(st, step, start=t, average=False,
+                           samples_per_frame=spf)
+        assert abs(ip2.start_time - t) < 1e-9
+        res2 = ip2.read(m)
+        np.testing.assert_allclose(res2['data'], res['data'][k:], rtol=1e-6)
+        np.testing.assert_array_equal(res2['count'], res['count'][k:])
+
+
+def test_integrate_times_wrong(bt):
+    data, src = fake_pulsar(bt)
+    with pytest.raises(ValueError):
+        bt.Integrate(src, start=src.start_time - 1.)
+    with pytest.raises(ValueError):
+        bt.Integrate(src, start=src.start_time + 3.)
+    with pytest.raises(AssertionError):
+        bt.Integrate(src, step=3600.)
+
+
+def test_fold_steps(bt):
+    """test_integration.py:262-330: step shorter and longer than the period."""
+    data, src = fake_pulsar(bt)
+    n_phase = 50
+
+    def phase(t):
+        return bt.to_float((t - src.start_time) * 80.) \
+            if hasattr(bt, 'to_float') else (t - src.start_time) * 80.
+
+    fh = bt.Fold(src, n_phase, phase, 10e-3, samples_per_frame=1,
+                 average=False)
+    fr = fh.read(3)
+    cnt = fr['count'].reshape(3, n_phase, -1)[..., 0]
+    dat = fr['data']
+    assert np.all(cnt.sum(1) == 100)
+    assert np.all((cnt[0, :40] == 3) | (cnt[0, :40] == 2))
+    assert np.all(cnt[0, 41:] == 0)
+    assert np.all(cnt[1, :30] != 0) and np.all(cnt[1, 40:] != 0)
+    assert np.all(cnt[1, 31:39] == 0)
+    assert np.all(dat[:, (0, 1, -1)].sum(1) > 10)
+    assert np.all(dat[:, 2:49] <= 0.125 * 3)
+    fh = bt.Fold(src, n_phase, phase, 30e-3, samples_per_frame=1,
+                 average=False)
+    fr = fh.read(10)
+    cnt = fr['count'].reshape(10, n_phase, -1)[..., 0]
+    assert np.all(cnt.sum(1) == 300)
+    dat = fr['data']
+    on = (0, 1, -1)
+    pulse_power = dat[:, on].sum(1) / cnt[:, on].sum(1)[:, None]
+    assert np.all(np.abs(pulse_power - 10. / 7.5 - 0.125) < 0.5)
+    np.testing.assert_allclose(dat[:, 2:-1] / cnt[:, 2:-1, None], 0.125,
+                               rtol=1e-5)
+    # with an offset start time
+    fh2 = bt.Fold(src, n_phase, phase, 30e-3, start=src.start_time + 30e-3,
+                  samples_per_frame=1, average=False)
+    fr2 = fh2.read(9)
+    np.testing.assert_array_equal(fr2['count'], fr['count'][1:])
+    np.testing.assert_allclose(fr2['data'], fr['data'][1:], rtol=1e-6)
+    # averaged (test_folding_with_averaging, test_non_integer_sample_rate_ratio)
+    fa = bt.Fold(src, n_phase, phase, 26e-3, samples_per_frame=20)
+    out = fa.read(10)
+    assert out.shape == (10, n_phase, 2)
+    np.testing.assert_allclose(out[:, 2:-1], 0.125, rtol=1e-6)
+    fb = bt.Fold(src, n_phase, phase, 1. / 3.)
+    out = fb.read()
+    assert out.shape[0] == 4
+    np.testing.assert_allclose(out[:, 2:-1], 0.125, rtol=1e-6)
