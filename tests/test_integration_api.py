@@ -113,8 +113,7 @@ def test_fold_steps(bt):
     n_phase = 50
 
     def phase(t):
-        return bt.to_float((t - src.start_time) * 80.) \
-            if hasattr(bt, 'to_float') else (t - src.start_time) * 80.
+        return (t - src.start_time) * 80.
 
     fh = bt.Fold(src, n_phase, phase, 10e-3, samples_per_frame=1,
                  average=False)
