@@ -41,6 +41,9 @@ class Channelize(TaskBase):
                  frequency=None, sideband=None):
         self._n = n = operator.index(n)
         samples_per_frame = operator.index(samples_per_frame)
+        # The check TaskBase makes (base.py:681-683), before any plan exists.
+        assert ih.shape[0] >= n * samples_per_frame, (
+            "not enough samples to fill one frame of spectra.")
         self._FFT = fft_maker.get()
         self._fft = self._FFT((samples_per_frame, n) + tuple(ih.sample_shape),
                               ih.dtype, axis=1, sample_rate=ih.sample_rate)
