@@ -153,3 +153,83 @@ def test_fold_steps(bt):
     out = fb.read()
     assert out.shape[0] == 4
     np.testing.assert_allclose(out[:, 2:-1], 0.125, rtol=1e-6)
+
+
+def test_fold_whole_and_part(bt):
+    """test_integration.py:355-392: fold everything, or from a start time."""
+    data, src = fake_pulsar(bt)
+    n_phase = 50
+
+    def phase(t):
+        return (t - src.start_time) * 80.
+
+    i = np.arange(16000)
+    i_phase = ((i / 1e4 * 80. * n_phase) % n_phase).astype(int)
+    expected = (np.bincount(i_phase, data[:, 0].astype('f8'))
+                / np.bincount(i_phase))
+    fh = bt.Fold(src, n_phase, phase)
+    assert abs(fh.stop_time - src.stop_time) < 1e-9
+    fr = fh.read(1)
+    np.testing.assert_allclose(fr[:, 2:-1], 0.125, rtol=1e-6)
+    np.testing.assert_allclose(fr[0, :, 0], expected, rtol=1e-5)
+    start = src.start_time + 1.
+    fh = bt.Fold(src, n_phase, phase, average=False, start=start)
+    assert abs(fh.start_time - start) < 1e-9
+    assert abs(fh.stop_time - src.stop_time) < 1e-9
+    fr = fh.read(1)
+    assert np.all(fr['count'].sum((0, 1)) == 6000)
+    average = fr['data'][0] / fr['count'][0].reshape(n_phase, -1)
+    np.testing.assert_allclose(average[2:-1], 0.125, rtol=1e-6)
+    with pytest.raises(ValueError):
+        bt.Fold(src, 8, phase, start=src.start_time - 1.)
+    with pytest.raises(ValueError):
+        bt.Fold(src, 8, phase, start=src.start_time + 3.)
+    with pytest.raises(AssertionError):
+        bt.Fold(src, 8, phase, step=3600.)
+
+
+@pytest.mark.parametrize('spf', [1, 160])
+def test_integrate_phase_steps(bt, spf):
+    """test_integration.py:406-425: 25 phase steps per cycle, 5 samples each."""
+    data, src = fake_pulsar(bt)
+
+    def phase(t):
+        return (t - src.start_time) * 80.
+
+    ref = data.reshape(-1, 5, 2).mean(1)
+    fh = bt.Integrate(src, 1. / 25, phase, samples_per_frame=spf)
+    assert fh.start_time == src.start_time
+    assert abs(fh.stop_time - src.stop_time) < 1e-9
+    assert fh.samples_per_frame == spf
+    np.testing.assert_allclose(fh.read(20), ref[:20], rtol=1e-6)
+    fh.seek(250)
+    np.testing.assert_allclose(fh.read(75), ref[250:325], rtol=1e-6)
+    if spf > 1:
+        np.testing.assert_allclose(fh.read(), ref[325:], rtol=1e-6)
+
+
+@pytest.mark.parametrize('spf', [1, 16])
+def test_pulse_stack_basics(bt, spf):
+    """test_integration.py:432-470."""
+    data, src = fake_pulsar(bt)
+
+    def phase(t):
+        return (t - src.start_time) * 80.
+
+    ref = data.reshape(-1, 25, 5, 2).mean(2)
+    fh = bt.PulseStack(src, 25, phase, samples_per_frame=spf)
+    assert fh.start_time == src.start_time
+    assert abs(fh.stop_time - src.stop_time) < 1e-9
+    assert fh.samples_per_frame == spf
+    fh.seek(5)
+    assert abs((fh.time - src.start_time) - 5 / 80.) < 1e-9
+    fh.seek(0)
+    np.testing.assert_allclose(fh.read(2), ref[:2], rtol=1e-6)
+    fh.seek(10)
+    np.testing.assert_allclose(fh.read(3), ref[10:13], rtol=1e-6)
+    np.testing.assert_allclose(fh.read(), ref[13:], rtol=1e-6)
+    # a slice of the input
+    ref2 = data[-360:-110].reshape(-1, 25, 5, 2).mean(2)
+    fh = bt.PulseStack(src[-360:-10], 25, phase, samples_per_frame=spf)
+    assert fh.shape == ref2.shape
+    np.testing.assert_allclose(fh.read(), ref2, rtol=1e-6)
