@@ -137,8 +137,13 @@ class Integrate(BaseTaskBase):
         n_sample = int(n_sample + 0.5 * self._mean_offset_size)
         assert n_sample >= 1, "time per frame larger than total time in stream"
         shape = (n_sample,) + tuple(ih.sample_shape)
-        # Without a phase the start is a time and the rate a frequency.
-        start_time = start if phase is None else False
+        # Without a phase the start is a time and the rate a frequency --
+        # unless the input itself counts in cycles (a phase-stepped Integrate
+        # or a PulseStack), in which case times come from it (the reference
+        # tells the two apart by the unit of the rate, integration.py:146-151).
+        in_cycles = phase is not None or getattr(ih, '_time_from_ih', False)
+        start_time = False if in_cycles else start
+        self._time_from_ih = in_cycles
 
         if dtype is None:
             if average:
@@ -543,6 +548,7 @@ class PulseStack(BaseTaskBase):
                          samples_per_frame=samples_per_frame,
                          dtype=dtype)
         self.n_phase = n_phase
+        self._time_from_ih = True    # one sample per cycle, not per second
 
     def _read_frame(self, frame_index):
         # Read the frame of the phase-binned stream directly.

@@ -49,9 +49,15 @@ class GetSlice(TaskBase):
         spf = min(ih.samples_per_frame, stop - start)
         super().__init__(ih, ih_samples_per_frame=spf, samples_per_frame=spf,
                          shape=(stop - start,) + sample_shape,
-                         start_time=ih.start_time + start / ih.sample_rate,
+                         start_time=ih._tell_time(start),
                          **meta)
         self._on_device = hasattr(ih, 'read_device')
+        self._time_from_ih = getattr(ih, '_time_from_ih', False)
+
+    def _tell_time(self, offset):
+        # Through the underlying stream (shaping.py:412-413): its samples need
+        # not be evenly spaced in time (phase-stepped Integrate, PulseStack).
+        return self.ih._tell_time(self._start + offset)
 
     def _read_data(self, count, out=None):
         data = self._ih_read(self._start + self.offset, count)

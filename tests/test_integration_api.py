@@ -233,3 +233,42 @@ def test_pulse_stack_basics(bt, spf):
     fh = bt.PulseStack(src[-360:-10], 25, phase, samples_per_frame=spf)
     assert fh.shape == ref2.shape
     np.testing.assert_allclose(fh.read(), ref2, rtol=1e-6)
+
+
+def test_pulse_stack_offset_slice_integrate(bt):
+    """test_integration.py:465-520."""
+    data, src = fake_pulsar(bt)
+
+    def phase(t):
+        return (t - src.start_time) * 80.
+
+    ref = data[124:-1].reshape(-1, 25, 5, 2).mean(2)
+    fh = bt.PulseStack(src, 25, phase, start=124)
+    assert abs((fh.start_time - src.start_time) - 124 / 1e4) < 1e-9
+    assert abs((fh.stop_time - src.stop_time) + 1 / 1e4) < 1e-9
+    np.testing.assert_allclose(fh.read(2), ref[:2], rtol=1e-6)
+    fh.seek(10)
+    assert abs((fh.time - src.start_time) - 124 / 1e4 - 10 / 80.) < 1e-9
+    np.testing.assert_allclose(fh.read(), ref[10:], rtol=1e-6)
+    for item in (slice(10, 100), slice(-10, None), slice(None, 10),
+                 slice(None), (slice(10, 100), 0)):
+        sliced = fh[item]
+        first = item[0] if isinstance(item, tuple) else item
+        start, stop, _ = first.indices(fh.shape[0])
+        t_start = 124 / 1e4 + start / 80.
+        assert abs((sliced.start_time - src.start_time) - t_start) < 1e-9
+        assert abs((sliced.stop_time - src.start_time)
+                   - 124 / 1e4 - stop / 80.) < 1e-9
+        sliced.seek(5)
+        assert abs((sliced.time - sliced.start_time) - 5 / 80.) < 1e-9
+        sliced.seek(0)
+        want = ref[item]
+        assert sliced.shape == want.shape
+        np.testing.assert_allclose(np.asarray(sliced.read()), want, rtol=1e-6)
+    # integrating a stack
+    fh = bt.PulseStack(src, 25, phase)
+    stack = fh.read(3)
+    ih = bt.Integrate(fh, 3)
+    np.testing.assert_allclose(ih.read(1)[0], stack.mean(0), rtol=1e-6)
+    assert ih.tell() == 1
+    assert abs((ih.time - src.start_time) - 3 / 80.) < 1e-9
