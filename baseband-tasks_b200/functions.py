@@ -14,41 +14,57 @@ from .base import TaskBase, simplify_shape
 __all__ = ['Square', 'Power']
 
 
-def _char_add(a, b):
-    return np.char.add(np.asarray(a, dtype=str), np.asarray(b, dtype=str))
+def _pair_labels(first, second):
+    """Element-wise concatenation of two arrays of polarization labels."""
+    return np.char.add(np.asarray(first, dtype=str),
+                       np.asarray(second, dtype=str))
 
 
-class Square(TaskBase):
-    """Converts samples to intensities by squaring.
+def _real_dtype(dtype):
+    """The real dtype matching a (possibly complex) sample dtype."""
+    dtype = np.dtype(dtype)
+    return np.dtype(f'f{dtype.itemsize // 2}') if dtype.kind == 'c' else dtype
+
+
+class _Detector(TaskBase):
+    """What `Square` and `Power` share: labels for the repr and a float
+    result, computed by one kernel over whatever block of frames is read."""
+    _on_device = True
+    _multi_frame = True
+
+    def _labels_from(self, ih):
+        raise NotImplementedError
+
+    def _repr_item(self, key, default, value=None):
+        # Labels derived from the input are the default, so they are not
+        # repeated in the repr (functions.py:52-55,125-129).
+        if key == 'polarization' and default is None \
+                and hasattr(self.ih, 'polarization'):
+            default = self._labels_from(self.ih)
+        return super()._repr_item(key, default=default, value=value)
+
+
+class Square(_Detector):
+    """Intensities: x**2 for real samples, |z|**2 for complex ones.
 
     Parameters
     ----------
     ih : task or stream reader
-        Input data stream.
-    polarization : array or (nested) list of char, optional
-        Output polarization labels.  By default, doubled labels from the
-        underlying stream (and ignored if not given).
+        The stream to detect.
+    polarization : array or nested list of str, optional
+        Labels of the output.  Default: each input label doubled ('X' ->
+        'XX'), or none if the input carries no labels.
     """
-    _on_device = True
-    _multi_frame = True
 
     def __init__(self, ih, polarization=None):
-        if polarization is None:
-            polarization = self._default_polarization(ih)
-        ih_dtype = np.dtype(ih.dtype)
-        self._complex = ih_dtype.kind == 'c'
-        dtype = np.zeros(1, dtype=ih_dtype).real.dtype
-        super().__init__(ih, dtype=dtype, polarization=polarization)
+        self._complex = np.dtype(ih.dtype).kind == 'c'
+        labels = polarization if polarization is not None \
+            else self._labels_from(ih)
+        super().__init__(ih, dtype=_real_dtype(ih.dtype), polarization=labels)
 
-    def _default_polarization(self, ih):
-        if not hasattr(ih, 'polarization'):
-            return None
-        return _char_add(ih.polarization, ih.polarization)
-
-    def _repr_item(self, key, default, value=None):
-        if key == 'polarization':
-            default = self._default_polarization(self.ih)
-        return super()._repr_item(key, default=default, value=value)
+    def _labels_from(self, ih):
+        pol = getattr(ih, 'polarization', None)
+        return None if pol is None else _pair_labels(pol, pol)
 
     def task(self, data, out=None):
         host = not B.is_tensor(data)
@@ -64,73 +80,60 @@ class Square(TaskBase):
         return _finish(result, out, host, self.dtype)
 
 
-class Power(TaskBase):
-    """Calculate powers and cross terms for two polarizations.
+class Power(_Detector):
+    """Powers and cross terms of a pair of polarizations.
 
-    For polarizations X and Y, 4 terms are produced: ``XX = |X|^2``,
-    ``YY = |Y|^2``, ``XY = Re(X conj Y)`` and ``YX = Im(X conj Y)``.
+    From X and Y the four products ``|X|^2``, ``|Y|^2``, ``Re(X conj Y)`` and
+    ``Im(X conj Y)`` are formed along the polarization axis, labelled 'XX',
+    'YY', 'XY' and 'YX' (functions.py:59-143).
 
     Parameters
     ----------
     ih : task or stream reader
-        Input data stream.
-    polarization : array or (nested) list of char, optional
-        Output polarization labels.  By default, inferred from the
-        underlying stream, using the scheme described above.
+        Complex stream with two polarizations along one axis.
+    polarization : array or nested list of str, optional
+        The four output labels, shaped so that they identify the polarization
+        axis.  Default: derived from the labels of ``ih`` as above; then
+        ``ih`` has to have them (`AttributeError` otherwise).
 
-    Raises
-    ------
-    AttributeError
-        If no polarization information is given.
-    ValueError
-        If the underlying stream is not complex, the number of polarizations
-        not equal to two, or the polarization labels not unique.
+    A `ValueError` is raised for real streams, for anything but two input
+    polarizations, and for output labels that are not four distinct ones
+    along a single axis.
     """
-    _on_device = True
-    _multi_frame = True
 
     def __init__(self, ih, polarization=None):
         if polarization is None:
-            polarization = self._default_polarization(ih)
+            labels = self._labels_from(ih)
         else:
-            polarization = simplify_shape(np.asanyarray(polarization))
-            if not (polarization.size == 4 == len(np.unique(polarization))
-                    and 4 in polarization.shape):
-                raise ValueError('output polarizations should have 4 unique '
-                                 'elements along one axis.')
-
-        self._axis = ih.ndim - polarization.ndim + polarization.shape.index(4)
-        if ih.shape[self._axis] != 2:
-            raise ValueError(f"input shape should be 2 along polarization axis"
-                             f" ({self._axis}), not {ih.shape[self._axis]}.")
-
-        shape = ih.shape[:self._axis] + (4,) + ih.shape[self._axis + 1:]
-        ih_dtype = np.dtype(ih.dtype)
-        if ih_dtype.kind != 'c':
-            raise ValueError("Power only works on a complex timestream.")
-        dtype = np.zeros(1, ih_dtype).real.dtype
-        super().__init__(ih, shape=shape, polarization=polarization,
-                         dtype=dtype)
+            labels = simplify_shape(np.asanyarray(polarization))
+            distinct = len(np.unique(labels))
+            if labels.size != 4 or distinct != 4 or 4 not in labels.shape:
+                raise ValueError("need 4 distinct output polarizations along "
+                                 "one axis.")
+        # Labels are aligned with the trailing axes of a sample.
+        axis = ih.ndim - labels.ndim + labels.shape.index(4)
+        if ih.shape[axis] != 2:
+            raise ValueError(f"axis {axis} of the input holds "
+                             f"{ih.shape[axis]} polarizations, not 2.")
+        if np.dtype(ih.dtype).kind != 'c':
+            raise ValueError("cross products need a complex stream.")
+        self._axis = axis
+        before, after = ih.shape[:axis], ih.shape[axis + 1:]
+        super().__init__(ih, shape=before + (4,) + after, polarization=labels,
+                         dtype=_real_dtype(ih.dtype))
         # Kernel view: (A, 2, B) -> (A, 4, B) with A including time.
-        self._inner = int(np.prod(ih.shape[self._axis + 1:], dtype=np.int64))
-        self._outer_per_sample = int(np.prod(ih.shape[1:self._axis],
-                                             dtype=np.int64))
+        self._inner = int(np.prod(after, dtype=np.int64))
+        self._outer_per_sample = int(np.prod(before[1:], dtype=np.int64))
 
-    def _default_polarization(self, ih):
-        if ih.polarization.size != 2:
-            raise ValueError("stream should have exactly 2 polarizations. "
-                             "Reshape appropriately.")
-        return _char_add(ih.polarization[[0, 1, 0, 1]],
-                         ih.polarization[[0, 1, 1, 0]])
-
-    def _repr_item(self, key, default, value=None):
-        if (key == 'polarization' and hasattr(self.ih, 'polarization')
-                and default is None):
-            default = self._default_polarization(self.ih)
-        return super()._repr_item(key, default=default, value=value)
+    def _labels_from(self, ih):
+        pol = ih.polarization        # AttributeError if there is none
+        if pol.size != 2:
+            raise ValueError("exactly 2 input polarizations are needed; "
+                             "reshape the stream first.")
+        return _pair_labels(pol[[0, 1, 0, 1]], pol[[0, 1, 1, 0]])
 
     def task(self, data, out=None):
-        """Calculate the polarization powers and cross terms."""
+        """The four products for a block of samples."""
         host = not B.is_tensor(data)
         x = B.as_device(data, dtype=np.complex64)
         n = x.shape[0]
