@@ -127,37 +127,48 @@ class Base:
 
     # ---------------------------------------------------------------- repr
     def _repr_item(self, key, default, value=None):
+        """``key=value`` for the repr, or None when there is nothing to show:
+        the value is unknown, or equal to the default of the argument."""
+        for name in (key, '_' + key):
+            if value is not None:
+                break
+            value = getattr(self, name, None)
         if value is None:
-            value = getattr(self, key, None)
-            if value is None:
-                value = getattr(self, '_' + key, None)
-                if value is None:
-                    return None
-        if default is not inspect._empty:
+            return None
+        if default is not inspect.Parameter.empty:
             try:
-                if np.all(value == default):
-                    return None
+                same = bool(np.all(value == default))
             except Exception:
-                pass
+                same = False
+            if same:
+                return None
         return f"{key}={value}".replace('\n', ',')
 
-    def __repr__(self):
-        name = self.__class__.__name__
+    def _repr_parameters(self):
+        """Constructor arguments of this class and, where it passes
+        ``**kwargs`` on, of the classes it inherits from, up to `Base`."""
         pars = {}
-        for cls in self.__class__.__mro__:
+        stopped_at = None
+        for cls in type(self).__mro__:
+            stopped_at = cls
             for key, par in inspect.signature(cls).parameters.items():
                 pars.setdefault(key, par)
-            if 'kwargs' not in pars or cls is Base:
+            if cls is Base or 'kwargs' not in pars:
                 break
-        overrides = [self._repr_item(key, par.default)
-                     for key, par in pars.items()]
-        if cls is Base and '__attributes__' in self.meta:
-            overrides.extend([self._repr_item(key, None)
-                              for key in self.meta['__attributes__'].keys()
-                              if key not in pars])
-        overrides = (',\n ' + ' ' * len(name)).join(
-            [override for override in overrides if override])
-        return f"{name}({overrides})"
+        return pars, stopped_at
+
+    def __repr__(self):
+        name = type(self).__name__
+        pars, last = self._repr_parameters()
+        items = [self._repr_item(key, par.default)
+                 for key, par in pars.items()]
+        if last is Base:
+            # Attributes set through **kwargs (frequency, sideband, ...).
+            items += [self._repr_item(key, None)
+                      for key in self.meta.get('__attributes__', {})
+                      if key not in pars]
+        indent = ',\n' + ' ' * (len(name) + 1)
+        return f"{name}({indent.join(item for item in items if item)})"
 
     # ---------------------------------------------------------- properties
     def _check_shape(self, value):
@@ -182,29 +193,28 @@ class Base:
 
     @property
     def size(self):
-        """Number of component samples in the output."""
-        prod = 1
-        for dim in self.shape:
-            prod *= dim
-        return prod
+        """Total number of values: samples times values per sample."""
+        return int(np.prod(self.shape, dtype=object)) if self.shape else 1
 
     @property
     def ndim(self):
-        """Number of dimensions of the output."""
+        """Number of axes of the stream seen as an array (time first)."""
         return len(self.shape)
 
     @property
     def dtype(self):
-        """Data type of the output."""
+        """numpy dtype of the samples that `read` returns."""
         return self._dtype
 
     @property
     def complex_data(self):
+        """Whether the samples are complex."""
         return self._dtype.kind == 'c'
 
     @property
     def sample_rate(self):
-        """Number of complete samples per second."""
+        """Complete samples per second (or per cycle, for phase-based
+        streams)."""
         return self._sample_rate
 
     @property
@@ -388,33 +398,31 @@ class BaseTaskBase(Base):
                  start_time=None, shape=None, sample_rate=None,
                  samples_per_frame=None, dtype=None, **kwargs):
         self.ih = ih
-        if ih_samples_per_frame is None:
-            ih_samples_per_frame = ih.samples_per_frame
-        self._ih_samples_per_frame = ih_samples_per_frame
-
-        shape = getattr_if_none(ih, 'shape', shape)
-        start_time = getattr_if_none(ih, 'start_time', start_time)
-        sample_rate = getattr_if_none(ih, 'sample_rate', sample_rate)
-        dtype = getattr_if_none(ih, 'dtype', dtype)
-        if samples_per_frame is None:
-            samples_per_frame = ih_samples_per_frame
-
+        self._ih_samples_per_frame = (ih.samples_per_frame
+                                      if ih_samples_per_frame is None
+                                      else ih_samples_per_frame)
+        # Whatever is not given is inherited from the input stream; its
+        # metadata are copied so that changing them here leaves ``ih`` alone.
+        given = dict(shape=shape, start_time=start_time,
+                     sample_rate=sample_rate, dtype=dtype)
+        inherited = {key: getattr_if_none(ih, key, value)
+                     for key, value in given.items()}
+        inherited['samples_per_frame'] = (self._ih_samples_per_frame
+                                          if samples_per_frame is None
+                                          else samples_per_frame)
         self.meta = _copy_meta(getattr(ih, 'meta', {}))
-        for attr in META_ATTRIBUTES:
+        for attr in META_ATTRIBUTES:     # frequency, sideband, polarization
             value = getattr_if_none(ih, attr, kwargs.pop(attr, None),
                                     required=False)
             if value is not None:
                 kwargs[attr] = value
-
-        super().__init__(shape=shape, start_time=start_time,
-                         sample_rate=sample_rate,
-                         samples_per_frame=samples_per_frame,
-                         dtype=dtype, **kwargs)
+        super().__init__(**inherited, **kwargs)
 
     def _repr_item(self, key, default, value=None):
-        if key == 'ih':
+        if key == 'ih':          # shown once, indented, below the arguments
             return 'ih'
         if default is None:
+            # Arguments left at what the input provides are not repeated.
             if key == 'samples_per_frame':
                 default = self._ih_samples_per_frame
             elif key == 'ih_samples_per_frame':
@@ -424,11 +432,11 @@ class BaseTaskBase(Base):
         return super()._repr_item(key, default=default, value=value)
 
     def __repr__(self):
-        base = super().__repr__()
-        if base.count('\n') == 1:
-            base = ' '.join(b.strip() for b in base.split('\n'))
-        return (base + "\nih: "
-                + "\n    ".join(repr(self.ih).split('\n')))
+        own = super().__repr__()
+        if own.count('\n') == 1:         # short enough for a single line
+            own = ' '.join(part.strip() for part in own.split('\n'))
+        below = repr(self.ih).replace('\n', '\n    ')
+        return f"{own}\nih: {below}"
 
     def _ih_read(self, start, count, device=None):
         """Input samples [start, start+count) as the task wants them."""
@@ -635,28 +643,30 @@ class Task(TaskBase):
 
     def __init__(self, ih, task, method=None, **kwargs):
         if method is None:
-            try:
-                argspec = inspect.getfullargspec(task)
-                narg = len(argspec.args)
-                if argspec.defaults:
-                    narg -= len(argspec.defaults)
-                if inspect.ismethod(task):
-                    narg -= 1
-                assert 1 <= narg <= 2
-                method = narg == 2
-            except Exception as exc:
-                exc.args += ("cannot determine whether ``task`` is a "
-                             "function or method. Pass in ``method``.",)
-                raise
-
-        if method:
-            self.task = types.MethodType(task, self)
-        else:
-            self.task = task
-
+            method = self._takes_stream(task)
+        # A two-argument callable is bound, so it sees the stream as `self`.
+        self.task = types.MethodType(task, self) if method else task
         super().__init__(ih, **kwargs)
 
+    @staticmethod
+    def _takes_stream(task):
+        """Whether ``task`` is called as ``task(stream, data)`` rather than
+        ``task(data)``: judged by its number of required positional
+        arguments, as the reference does (base.py:856-871)."""
+        try:
+            params = [p for p in inspect.signature(task).parameters.values()
+                      if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)
+                      and p.default is p.empty]
+        except (TypeError, ValueError) as exc:
+            raise TypeError("cannot inspect ``task``; pass ``method`` to say "
+                            "whether it takes the stream as well.") from exc
+        if len(params) not in (1, 2):
+            raise TypeError("``task`` should take (data) or (stream, data); "
+                            "pass ``method`` if it is something else.")
+        return len(params) == 2
+
     def _repr_item(self, key, default, value=None):
+        # Show the function itself, not the bound method made from it.
         if key == 'task' and isinstance(self.task, types.MethodType):
             value = self.task.__func__
         return super()._repr_item(key, default=default, value=value)
