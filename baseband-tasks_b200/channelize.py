@@ -49,17 +49,16 @@ class Channelize(TaskBase):
                               ih.dtype, axis=1, sample_rate=ih.sample_rate)
         self._ffts = {samples_per_frame: self._fft}
 
-        frequency = getattr_if_none(ih, 'frequency', frequency, required=False)
-        sideband = getattr_if_none(ih, 'sideband', sideband, required=False)
-        if frequency is not None:
-            frequency = frequency + self._fft.frequency * sideband
-
-        sample_rate = ih.sample_rate / n
-        shape = (-1,) + self._fft.frequency_shape[1:]
-        super().__init__(ih, shape=shape, sample_rate=sample_rate,
+        # Channel frequencies in FFT order, on either side of each input
+        # frequency according to its sideband (channelize.py:60-64).
+        f_in = getattr_if_none(ih, 'frequency', frequency, required=False)
+        sb_in = getattr_if_none(ih, 'sideband', sideband, required=False)
+        f_out = None if f_in is None else f_in + self._fft.frequency * sb_in
+        super().__init__(ih, shape=(-1,) + self._fft.frequency_shape[1:],
+                         sample_rate=ih.sample_rate / n,
                          samples_per_frame=samples_per_frame,
-                         frequency=frequency, sideband=sideband,
-                         dtype=self._fft.frequency_dtype)
+                         dtype=self._fft.frequency_dtype,
+                         frequency=f_out, sideband=sb_in)
 
     def _fft_for(self, n_spec):
         fft = self._ffts.get(n_spec)
@@ -104,38 +103,32 @@ class Dechannelize(TaskBase):
     def __init__(self, ih, n=None, samples_per_frame=None, *,
                  dtype=None, frequency=None, sideband=None):
         assert ih.complex_data, "Dechannelization needs complex spectra."
-        if dtype is None:
-            dtype = ih.dtype
-        dtype = np.dtype(dtype)
-        if n is None:
-            if dtype.kind == 'c':
-                n = ih.sample_shape[0]
-            else:
-                raise ValueError("need explicit 'n' for real transform.")
-        else:
+        dtype = np.dtype(ih.dtype if dtype is None else dtype)
+        if n is not None:
             n = operator.index(n)
-
-        if samples_per_frame is None:
-            ih_samples_per_frame = ih.samples_per_frame
+        elif dtype.kind == 'c':
+            n = ih.sample_shape[0]      # complex: as many samples as channels
         else:
-            ih_samples_per_frame = max(int(round(samples_per_frame / n)), 1)
+            raise ValueError("a real-valued output needs the number of "
+                             "samples per spectrum, 'n'.")
+        # Frames hold whole spectra: at least one.
+        ih_samples_per_frame = (ih.samples_per_frame
+                                if samples_per_frame is None
+                                else max(int(round(samples_per_frame / n)), 1))
 
         self._FFT = fft_maker.get()
         self._ifft = self._FFT((ih_samples_per_frame, n)
                                + tuple(ih.sample_shape[1:]),
                                dtype=dtype, axis=1, direction='backward')
         self._iffts = {ih_samples_per_frame: self._ifft}
-        sample_rate = ih.sample_rate * n
-
-        if frequency is None and getattr(ih, 'frequency', None) is not None:
-            frequency = ih.frequency[0]
-
-        super().__init__(ih, shape=(-1,) + tuple(ih.shape[2:]),
-                         sample_rate=sample_rate,
-                         ih_samples_per_frame=ih_samples_per_frame,
-                         frequency=frequency, sideband=sideband,
-                         dtype=self._ifft.time_dtype)
         self._n = n
+        if frequency is None and getattr(ih, 'frequency', None) is not None:
+            frequency = ih.frequency[0]      # the zero-frequency channel
+        super().__init__(ih, ih_samples_per_frame=ih_samples_per_frame,
+                         shape=(-1,) + tuple(ih.shape[2:]),
+                         sample_rate=ih.sample_rate * n,
+                         dtype=self._ifft.time_dtype,
+                         frequency=frequency, sideband=sideband)
 
     def task(self, data, out=None):
         n_spec = data.shape[0]
