@@ -53,34 +53,35 @@ class FFTBase:
         """Transform ``a`` along ``axis``."""
         return self._fft(a)
 
+    _DESCRIPTION = ('direction', 'time_shape', 'time_dtype', 'frequency_shape',
+                    'frequency_dtype', 'axis', 'ortho', 'sample_rate')
+
     def inverse(self):
         """The same transform in the opposite direction."""
-        return self.__class__(
-            direction=('forward' if self.direction == 'backward'
-                       else 'backward'))
+        flipped = {'forward': 'backward', 'backward': 'forward'}
+        return type(self)(direction=flipped[self.direction])
 
     def __copy__(self):
-        return self.__class__(direction=self.direction)
+        return type(self)(direction=self.direction)
 
     def __eq__(self, other):
-        return (self.direction == other.direction
-                and self.time_shape == other.time_shape
-                and self.time_dtype == other.time_dtype
-                and self.frequency_shape == other.frequency_shape
-                and self.frequency_dtype == other.frequency_dtype
-                and self.axis == other.axis
-                and self.ortho == other.ortho
-                and self.sample_rate == other.sample_rate)
+        # Two transforms are equal if everything that describes them is.
+        try:
+            return all(getattr(self, name) == getattr(other, name)
+                       for name in self._DESCRIPTION)
+        except AttributeError:
+            return NotImplemented
+
+    __hash__ = None
 
     def __repr__(self):
-        return ("<{s.__class__.__name__}"
-                " direction={s.direction},\n"
-                "    axis={s.axis}, ortho={s.ortho},"
-                " sample_rate={s.sample_rate}\n"
-                "    Time domain: shape={s.time_shape},"
-                " dtype={s.time_dtype}\n"
-                "    Frequency domain: shape={s.frequency_shape},"
-                " dtype={s.frequency_dtype}>".format(s=self))
+        return (f"<{type(self).__name__} direction={self.direction},\n"
+                f"    axis={self.axis}, ortho={self.ortho}, "
+                f"sample_rate={self.sample_rate}\n"
+                f"    Time domain: shape={self.time_shape}, "
+                f"dtype={self.time_dtype}\n"
+                f"    Frequency domain: shape={self.frequency_shape}, "
+                f"dtype={self.frequency_dtype}>")
 
 
 class FFTMakerMeta(type):
@@ -106,38 +107,35 @@ class FFTMakerBase(metaclass=FFTMakerMeta):
 
     def __call__(self, shape, dtype, direction='forward', axis=0, ortho=False,
                  sample_rate=None, **kwargs):
-        time_shape = tuple(shape)
-        time_dtype = np.dtype(dtype)
+        time_shape, time_dtype = tuple(shape), np.dtype(dtype)
         axis = operator.index(axis)
         frequency_shape, frequency_dtype = self.get_frequency_data_info(
             time_shape, time_dtype, axis=axis)
-        attributes = dict(
-            _time_shape=time_shape,
-            _time_dtype=time_dtype,
-            _frequency_shape=frequency_shape,
-            _frequency_dtype=frequency_dtype,
-            _axis=axis,
-            _ortho=bool(ortho),
-            _sample_rate=sample_rate)
-        for key, value in kwargs.items():
-            attributes['_' + key] = value
+        # The transform is an instance of a class made on the spot, with the
+        # description of the data as (private) class attributes, so that
+        # ``inverse()`` and ``copy`` only need the direction
+        # (fourier/base.py:262-311).
+        described = dict(time_shape=time_shape, time_dtype=time_dtype,
+                         frequency_shape=frequency_shape,
+                         frequency_dtype=frequency_dtype, axis=axis,
+                         ortho=bool(ortho), sample_rate=sample_rate, **kwargs)
         cls = type(self._FFTBase.__name__.replace('Base', ''),
-                   (self._FFTBase,), attributes)
+                   (self._FFTBase,),
+                   {'_' + key: value for key, value in described.items()})
         return cls(direction)
 
     def get_frequency_data_info(self, shape, dtype, axis=0):
-        """Shape and dtype of the frequency-domain array."""
-        if dtype.kind == 'f':
-            frequency_shape = list(shape)
-            frequency_shape[axis] = shape[axis] // 2 + 1
-            frequency_dtype = np.dtype('c{0:d}'.format(2 * dtype.itemsize))
-            return tuple(frequency_shape), frequency_dtype
-        return shape, dtype
+        """Shape and dtype of the frequency-domain array: real data keep the
+        ``n // 2 + 1`` non-negative frequencies and become complex."""
+        if dtype.kind != 'f':
+            return shape, dtype
+        half = shape[:axis] + (shape[axis] // 2 + 1,) + shape[axis + 1:]
+        return tuple(half), np.dtype(f'c{2 * dtype.itemsize}')
 
     def __repr__(self):
-        return '{}({})'.format(self.__class__.__name__,
-                               ', '.join(['{}={}'.format(k, v) for k, v
-                                          in self._repr_kwargs.items()]))
+        settings = ', '.join(f'{key}={value}'
+                             for key, value in self._repr_kwargs.items())
+        return f'{type(self).__name__}({settings})'
 
 
 class _StateContext:
