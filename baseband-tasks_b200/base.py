@@ -23,7 +23,7 @@ import warnings
 import numpy as np
 
 from . import _buffers as B
-from ._units import to_float
+from ._units import is_index, to_float
 
 __all__ = ['Base', 'BaseTaskBase', 'TaskBase', 'PaddedTaskBase',
            'SetAttribute', 'Task', 'META_ATTRIBUTES', 'check_broadcast_to',
@@ -94,23 +94,27 @@ class Base:
         if 'meta' not in self.__dict__:
             self.meta = {}
 
-        if len({'frequency', 'sideband'}.difference(kwargs)) == 1:
-            raise ValueError('frequency and sideband should both '
-                             'be passed in.')
+        self._set_attributes(kwargs)
 
-        attributes = {}
-        for attr, value in kwargs.items():
-            if attr in META_ATTRIBUTES:
-                if value is not None:
-                    if attr == 'sideband':
-                        value = np.where(np.asanyarray(value) > 0,
-                                         np.int8(1), np.int8(-1))
-                    attributes[attr] = self._check_shape(value)
-            else:
-                raise TypeError('__init__() got unexpected keyword argument '
-                                f'{attr!r}')
-        if attributes:
-            self.meta.setdefault('__attributes__', {}).update(attributes)
+    def _set_attributes(self, given):
+        """Store frequency, sideband and polarization in the metadata, each
+        checked to broadcast against a sample (base.py:148-169)."""
+        unknown = set(given) - META_ATTRIBUTES
+        if unknown:
+            raise TypeError("__init__() got unexpected keyword argument "
+                            f"{sorted(unknown)[0]!r}")
+        if ('frequency' in given) != ('sideband' in given):
+            raise ValueError("frequency and sideband go together: pass both.")
+        checked = {}
+        for name, value in given.items():
+            if value is None:
+                continue
+            if name == 'sideband':     # stored as +1 / -1
+                value = np.where(np.asanyarray(value) > 0,
+                                 np.int8(1), np.int8(-1))
+            checked[name] = self._check_shape(value)
+        if checked:
+            self.meta.setdefault('__attributes__', {}).update(checked)
 
     def __getattr__(self, attr):
         if attr in META_ATTRIBUTES:
@@ -239,26 +243,25 @@ class Base:
         ``offset`` is a number of samples, a time offset or an absolute time;
         for the latter two the pointer moves to the nearest sample.
         """
-        try:
-            offset = operator.index(offset)
-        except Exception:
+        if not is_index(offset):
+            # A time: absolute if the start time can be subtracted from it
+            # (then ``whence`` does not apply), otherwise an interval.
             try:
                 offset = offset - self.start_time
+                whence = 0
             except Exception:
                 pass
-            else:
-                whence = 0
             offset = int(np.round(to_float(offset * self.sample_rate)))
-
-        if whence == 0 or whence == 'start':
-            self.offset = offset
-        elif whence == 1 or whence == 'current':
-            self.offset += offset
-        elif whence == 2 or whence == 'end':
-            self.offset = self.shape[0] + offset
         else:
-            raise ValueError("invalid 'whence'; should be 0 or 'start', 1 or "
+            offset = operator.index(offset)
+
+        origin = {0: 0, 'start': 0,
+                  1: self.offset, 'current': self.offset,
+                  2: self.shape[0], 'end': self.shape[0]}
+        if whence not in origin:
+            raise ValueError("'whence' should be 0 or 'start', 1 or "
                              "'current', or 2 or 'end'.")
+        self.offset = origin[whence] + offset
         return self.offset
 
     def tell(self, unit=None):
@@ -469,39 +472,42 @@ class TaskBase(BaseTaskBase):
     def __init__(self, ih, *, ih_samples_per_frame=None,
                  shape=None, sample_rate=None, samples_per_frame=None,
                  **kwargs):
+        # Input samples per output sample.
         if sample_rate is None:
-            sample_rate = ih.sample_rate
-            sample_rate_ratio = 1.
+            sample_rate, ratio = ih.sample_rate, 1.
         else:
-            sample_rate_ratio = to_float(ih.sample_rate / sample_rate)
-        if samples_per_frame is None:
+            ratio = to_float(ih.sample_rate / sample_rate)
+
+        def whole(number, what):
+            assert number % 1 == 0, f"inferred {what} must be integer"
+            return int(number)
+
+        # Frame sizes on either side follow from one another through the
+        # rate ratio; with neither given, the input's framing is kept.
+        if samples_per_frame is not None:
+            if ih_samples_per_frame is None:
+                ih_samples_per_frame = whole(samples_per_frame * ratio,
+                                             "input samples per frame")
+        else:
             if ih_samples_per_frame is None:
                 ih_samples_per_frame = ih.samples_per_frame
-            samples_per_frame = ih_samples_per_frame / sample_rate_ratio
-            assert samples_per_frame % 1 == 0, (
-                "inferred samples per frame must be integer")
-            samples_per_frame = int(samples_per_frame)
-        elif ih_samples_per_frame is None:
-            ih_samples_per_frame = samples_per_frame * sample_rate_ratio
-            assert ih_samples_per_frame % 1 == 0, (
-                "inferred input samples per frame must be integer")
-            ih_samples_per_frame = int(ih_samples_per_frame)
-
+            samples_per_frame = whole(ih_samples_per_frame / ratio,
+                                      "samples per frame")
         assert ih_samples_per_frame <= ih.shape[0], (
             "time per frame larger than total time in stream")
 
+        # Only complete frames are offered (base.py:685-688).
         if shape is None or shape[0] == -1:
-            ns = ((ih.shape[0] // ih_samples_per_frame)
-                  * samples_per_frame)
-            shape = (ns,) + (ih.shape[1:] if shape is None
-                             else tuple(shape[1:]))
+            n_frames = ih.shape[0] // ih_samples_per_frame
+            tail = ih.shape[1:] if shape is None else tuple(shape[1:])
+            shape = (n_frames * samples_per_frame,) + tail
 
         super().__init__(ih=ih, ih_samples_per_frame=ih_samples_per_frame,
                          shape=shape, sample_rate=sample_rate,
-                         samples_per_frame=samples_per_frame,
-                         **kwargs)
-        alignment = max(1, int(sample_rate_ratio))
-        self._ih_stop = (self.ih.shape[0] // alignment) * alignment
+                         samples_per_frame=samples_per_frame, **kwargs)
+        # Input beyond the last whole output sample is never read.
+        per_output = max(1, int(ratio))
+        self._ih_stop = (self.ih.shape[0] // per_output) * per_output
 
     def _seek_frame(self, frame_index):
         return self.ih.seek(frame_index * self._ih_samples_per_frame)
@@ -581,46 +587,42 @@ class PaddedTaskBase(TaskBase):
 
     def __init__(self, ih, pad_start=0, pad_end=0, *,
                  samples_per_frame=None, next_fast_len=None, **kwargs):
-        self._pad_start = operator.index(pad_start)
-        self._pad_end = operator.index(pad_end)
-        if self._pad_start < 0 or self._pad_end < 0:
-            raise ValueError("padding values must be 0 or positive.")
-
-        pad = self._pad_start + self._pad_end
-        if samples_per_frame is None:
-            ih_samples_per_frame = max(ih.samples_per_frame, pad * 4)
-        else:
-            ih_samples_per_frame = samples_per_frame + pad
-
+        pads = (operator.index(pad_start), operator.index(pad_end))
+        if min(pads) < 0:
+            raise ValueError("padding cannot be negative.")
+        self._pad_start, self._pad_end = pads
+        pad = sum(pads)
+        # Input frame: what was asked for plus the padding or, by default,
+        # at least four times the padding (so that at most a quarter of the
+        # arithmetic is thrown away), rounded up to a length the FFT likes
+        # (base.py:752-760).
+        n_in = (samples_per_frame + pad if samples_per_frame is not None
+                else max(ih.samples_per_frame, 4 * pad))
         if next_fast_len:
-            ih_samples_per_frame = next_fast_len(ih_samples_per_frame)
-
-        samples_per_frame = ih_samples_per_frame - pad
-
-        if pad > samples_per_frame:
-            warnings.warn("task will be inefficient; for {} samples "
-                          "per frame, more ({}) will be added for padding."
-                          .format(samples_per_frame, pad))
-
-        n_sample = ih.shape[0] - pad
-        shape = (n_sample,) + tuple(ih.sample_shape)
-        kwargs['start_time'] = (getattr_if_none(ih, 'start_time', **kwargs)
-                                + self._pad_start / ih.sample_rate)
-        super().__init__(ih, ih_samples_per_frame=ih_samples_per_frame,
-                         shape=shape, samples_per_frame=samples_per_frame,
+            n_in = next_fast_len(n_in)
+        n_out = n_in - pad
+        if n_out < pad:
+            warnings.warn(f"inefficient task: each frame of {n_out} samples "
+                          f"needs {pad} more for padding.")
+        # The output starts pad_start samples into the input and is shorter
+        # by the total padding.
+        t0 = getattr_if_none(ih, 'start_time', **kwargs)
+        kwargs['start_time'] = t0 + self._pad_start / ih.sample_rate
+        super().__init__(ih, ih_samples_per_frame=n_in,
+                         samples_per_frame=n_out,
+                         shape=(ih.shape[0] - pad,) + tuple(ih.sample_shape),
                          **kwargs)
 
     _frame_offset = 0
 
     def _seek_frame(self, frame_index):
-        ih_index = frame_index * self.samples_per_frame
-        max_start = self.ih.shape[0] - self._ih_samples_per_frame
-        if ih_index > max_start:
-            self._frame_offset = ih_index - max_start
-            return self.ih.seek(max_start)
-        else:
-            self._frame_offset = 0
-            return self.ih.seek(ih_index)
+        # Frame i reads input from i * samples_per_frame; a last frame that
+        # would run off the end is moved back to end exactly there, and the
+        # samples it then repeats are skipped (base.py:775-790).
+        wanted = frame_index * self.samples_per_frame
+        last_start = self.ih.shape[0] - self._ih_samples_per_frame
+        self._frame_offset = max(0, wanted - last_start)
+        return self.ih.seek(min(wanted, last_start))
 
     def _get_frame(self, offset):
         self._frame, sample_offset = super()._get_frame(offset)
