@@ -57,7 +57,8 @@ _SIGNATURES = {
                                    c_void_p, c_int64, c_int64, c_void_p,
                                    c_void_p, c_int, c_void_p]),
     'bbt_fold_exec': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64,
-                              c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                              c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                              c_void_p,
                               POINTER(c_double), c_int, c_double, c_double,
                               c_int, c_void_p, c_void_p, c_void_p]),
     'bbt_pfb_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64,

@@ -276,6 +276,19 @@ class Base:
     def _tell_time(self, offset):
         return self._start_time + offset / self.sample_rate
 
+    def _sample_grid(self):
+        """``(time, index)``: sample 0 of this stream is sample ``index`` (an
+        exact integer) of a grid of samples at this stream's rate that
+        starts at ``time``.
+
+        Tasks that only cut, pad or relabel their input keep its grid and
+        add their whole-sample shift, so that every block of a stream shared
+        out in time (`baseband_tasks_b200.parallel`) counts its samples on
+        the grid of the whole observation; `Fold` evaluates pulse phases from
+        these indices, which makes the phase bins independent of the cut.
+        """
+        return self.start_time, 0
+
     # -------------------------------------------------------------- reading
     def read(self, count=None, out=None):
         """Read a number of complete samples into a numpy array.
@@ -441,6 +454,17 @@ class BaseTaskBase(Base):
         below = repr(self.ih).replace('\n', '\n    ')
         return f"{own}\nih: {below}"
 
+    # Whole samples between sample 0 of this stream and sample 0 of ``ih``
+    # for tasks that keep the sampling of their input; None if not tied.
+    _grid_shift = None
+
+    def _sample_grid(self):
+        shift = self._grid_shift
+        if shift is None or not hasattr(self.ih, '_sample_grid'):
+            return super()._sample_grid()
+        time, index = self.ih._sample_grid()
+        return time, index + shift
+
     def _ih_read(self, start, count, device=None):
         """Input samples [start, start+count) as the task wants them."""
         self.ih.seek(start)
@@ -591,6 +615,7 @@ class PaddedTaskBase(TaskBase):
         if min(pads) < 0:
             raise ValueError("padding cannot be negative.")
         self._pad_start, self._pad_end = pads
+        self._grid_shift = self._pad_start
         pad = sum(pads)
         # Input frame: what was asked for plus the padding or, by default,
         # at least four times the padding (so that at most a quarter of the
@@ -685,6 +710,8 @@ class SetAttribute(TaskBase):
                  **kwargs):
         super().__init__(ih, start_time=start_time, sample_rate=sample_rate,
                          **kwargs)
+        if start_time is None and sample_rate is None:
+            self._grid_shift = 0
         if not set(kwargs).difference(META_ATTRIBUTES):
             self.read = self.simple_read
             self.read_device = self.simple_read_device

@@ -169,7 +169,8 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
 }
 
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
-                  int64_t i_first, const int64_t* lo, const int64_t* hi,
+                  int64_t i_first, int64_t i_phase, const int64_t* lo,
+                  const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,
                   const double* coef, int ncoef, double i_ref, double rate,
                   int n_phase, void* sum, void* count, void* stream) {
@@ -190,6 +191,7 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
   a.inner = inner;
   a.n = n;
   a.i_first = i_first;
+  a.i_phase = i_phase;
   a.b_first = b_first;
   a.i_ref = i_ref;
   a.rate = rate;

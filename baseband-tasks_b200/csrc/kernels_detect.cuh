@@ -259,7 +259,7 @@ BBT_GLOBAL void integrate_kernel(IntegrateArgs a) {
 // Fold: for every sample i of time bin b, phase bin
 //   p = int(((phase(i) mod 1) * n_phase))        (integration.py:389-391)
 // and sum[b][p][c] += x[i][c], count[b][p] += 1  (integration.py:394-395).
-// phase(i) = Horner(coef, dt), dt = (double(i_abs) - i_ref) / rate, all in float64
+// phase(i) = Horner(coef, dt), dt = (double(i_phase + i) - i_ref) / rate, all in float64
 // with individually rounded operations (no FMA), so that the bin assignment
 // is bit-identical to the oracle's numpy arithmetic.  Alternatively the phase
 // bins may be supplied precomputed (pbin != nullptr) for arbitrary callables.
@@ -274,6 +274,8 @@ struct FoldArgs {
   const int* pbin;            // optional precomputed phase bins [n]
   long long inner;            // floats per sample in the output
   long long n, i_first;       // samples in this call; absolute index of first
+  long long i_phase;          // index of the first sample on the grid the
+                              // phase polynomial counts on (i_ref refers to it)
   long long b_first;          // time bin of blockIdx.y = 0
   double i_ref;               // sample index (may be fractional) at which dt = 0
   double rate;
@@ -464,7 +466,7 @@ BBT_DEV void fold_four(const FoldArgs& a, float* hist, unsigned* hcnt,
   constexpr long long step = (long long)kFoldThreads * kFoldUnroll;
   long long ib = i0 + (threadIdx.x - lane);
   // Sample indices as doubles: integers below 2^53 add exactly.
-  double xd = (double)(a.i_first + ib + lane);
+  double xd = (double)(a.i_phase + ib + lane);
   for (; ib + step - kFoldThreads + 32 <= i1; ib += step, xd += (double)step)
     fold_four_tile<POWER, false>(a, f, hist, hcnt, ib, i1, xd, lane, acc, acc_n, cur);
   if (ib < i1)
@@ -562,7 +564,7 @@ BBT_DEV void fold_four_staged(const FoldArgs& a, float* hist, unsigned* hcnt,
     __syncwarp();  // the warp has taken its samples: the stage is free
     const long long knext = kt + (long long)kFoldStages * NW;
     if (lane == 0 && knext < nt) issue(knext, s);
-    const double xd = (double)(a.i_first + first + lane);
+    const double xd = (double)(a.i_phase + first + lane);
     if (whole)
       fold_four_bins<POWER, false, 32>(a, f, hist, hcnt, x, first, i1, xd, lane,
                                        acc, acc_n, cur);
@@ -632,7 +634,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(kFoldThreads, 4) fold_kernel(FoldArgs a) {
 #pragma unroll
       for (int c = 0; c < kFoldFast; ++c) x[c] = 0.f;
       if (ok) {
-        p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
+        p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_phase + i);
         if (p < 0) p = 0;
         if (p >= a.n_phase) p = a.n_phase - 1;
         if (POWER) {
@@ -697,7 +699,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(kFoldThreads, 4) fold_kernel(FoldArgs a) {
 #endif
   {
     for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-      int p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_first + i);
+      int p = a.pbin ? a.pbin[i] : fold_phase_bin(a, a.i_phase + i);
       if (p < 0) p = 0;
       if (p >= a.n_phase) p = a.n_phase - 1;
       float* dsum = (a.use_smem ? hist : gsum) + (long long)p * a.inner;

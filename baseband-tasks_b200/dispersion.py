@@ -110,6 +110,7 @@ class Disperse(PaddedTaskBase):
         self._dm = dm
         self.reference_frequency = reference_frequency
         self._sample_offset = sample_offset
+        self._grid_shift = self._pad_start + sample_offset
         self._pad_slice = slice(self._pad_start,
                                 self._pad_start + self.samples_per_frame)
         self._rate_mhz = rate_mhz

@@ -31,6 +31,7 @@ class _Detector(TaskBase):
     result, computed by one kernel over whatever block of frames is read."""
     _on_device = True
     _multi_frame = True
+    _grid_shift = 0      # sample k of the output is sample k of the input
 
     def _labels_from(self, ih):
         raise NotImplementedError

@@ -91,11 +91,21 @@ class ArrayStream(Base):
 
     Reads return views of the data; with a device tensor the samples are
     already in HBM and downstream GPU tasks use them in place.
+
+    ``grid=(time, index)`` states that the array is a block of a longer
+    stream: its first sample is sample ``index`` of a stream that started at
+    ``time`` (``start_time`` is then ``time + index / sample_rate``).  Tasks
+    that number samples (`Fold` with a `PolynomialPhase`) count on that grid,
+    so every block of a stream shared out over GPUs gets the bins the whole
+    stream would.
     """
 
     def __init__(self, data, start_time, sample_rate, samples_per_frame=None,
-                 **kwargs):
+                 grid=None, **kwargs):
         self._data = data
+        self._grid = grid
+        if grid is not None and start_time is None:
+            start_time = grid[0] + grid[1] / sample_rate
         if B.is_tensor(data):
             dtype = np.dtype(str(data.dtype).replace('torch.', ''))
         else:
@@ -106,6 +116,11 @@ class ArrayStream(Base):
                          sample_rate=sample_rate,
                          samples_per_frame=samples_per_frame, dtype=dtype,
                          **kwargs)
+
+    def _sample_grid(self):
+        if self._grid is None:
+            return super()._sample_grid()
+        return self._grid[0], int(self._grid[1])
 
     def _read_data(self, count, out=None):
         data = self._data[self.offset:self.offset + count]

@@ -43,6 +43,11 @@ class PolynomialPhase:
     ``dt = (float64(i) - i_ref) / sample_rate`` with Horner's rule and
     individually rounded float64 operations -- `of_index` is the same
     arithmetic in numpy (the documented time convention for bit-exact bins).
+    Here ``i`` counts samples on the grid of the whole observation
+    (``Base._sample_grid``: tasks that cut or pad a stream pass the grid of
+    their input on with an exact integer shift), and ``i_ref`` is the index on
+    that grid at which ``dt`` is zero; a block of a stream shared out in time
+    therefore gets the very same bins as the whole stream would.
     """
 
     def __init__(self, coef, reference_time):
@@ -63,9 +68,16 @@ class PolynomialPhase:
         return phase
 
     def i_ref(self, start_time, sample_rate):
-        """Stream sample index (fractional) at which ``dt`` is zero."""
+        """Index (fractional) at which ``dt`` is zero on a grid of samples
+        that starts at ``start_time``."""
         return float(to_float((self.reference_time - start_time)
                               * sample_rate))
+
+    def grid(self, stream):
+        """``(i_ref, i_0)`` for folding ``stream``: the index of the reference
+        time and of the stream's first sample on the stream's sample grid."""
+        time, index = stream._sample_grid()
+        return self.i_ref(time, stream.sample_rate), index
 
     def of_index(self, index, i_ref, sample_rate):
         rate = float(to_float(sample_rate * 1.))
@@ -475,7 +487,7 @@ class Fold(Integrate):
         poly = self.phase if isinstance(self.phase, PolynomialPhase) else None
         if poly is not None:
             rate = float(to_float(ih.sample_rate * 1.))
-            i_ref = poly.i_ref(ih.start_time, ih.sample_rate)
+            i_ref, i_grid = poly.grid(ih)
             coef = poly.coef
             coef_p = coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         pos = start
@@ -507,13 +519,14 @@ class Fold(Integrate):
                 if poly is None:
                     lib.check(lib.bbt_fold_exec(
                         B.ptr(x), int(self._fused == 'power'), n, inner, pos,
-                        B.ptr(d_lo), B.ptr(d_hi), bb, nb, B.ptr(d_pbin),
+                        pos, B.ptr(d_lo), B.ptr(d_hi), bb, nb, B.ptr(d_pbin),
                         None, 0, 0., 1., self.n_phase, B.ptr(sums),
                         B.ptr(count), _cabi.stream_ptr()))
                 else:
                     lib.check(lib.bbt_fold_exec(
                         B.ptr(x), int(self._fused == 'power'), n, inner, pos,
-                        B.ptr(d_lo), B.ptr(d_hi), bb, nb, None, coef_p,
+                        pos + i_grid, B.ptr(d_lo), B.ptr(d_hi), bb, nb, None,
+                        coef_p,
                         len(coef), i_ref, rate, self.n_phase, B.ptr(sums),
                         B.ptr(count), _cabi.stream_ptr()))
             pos = nxt

@@ -35,6 +35,7 @@ class GetSlice(TaskBase):
         if not 0 <= start < stop <= ih.shape[0]:
             raise IndexError("slice is empty or out of range.")
         self._start, self._stop = start, stop
+        self._grid_shift = start
         self._sample_item = (slice(None),) + tuple(sample_item)
         probe = np.empty((1,) + tuple(ih.sample_shape), np.int8)
         sample_shape = probe[self._sample_item].shape[1:]

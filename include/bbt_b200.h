@@ -135,14 +135,18 @@ int bbt_integrate_exec(const void* in, int64_t n, int64_t inner,
  * covers absolute samples [lo[b], hi[b]) (device int64; the host applies the
  * reference's searchsorted convention).  Phase bins come either from pbin
  * (device int32 per sample of this call) or from the float64 polynomial
- * phase(i) = sum_k coef[k] ((i - i_ref)/rate)^k (i_ref: sample index, possibly
- * fractional, at which the polynomial's time argument is zero) evaluated in
- * float64 by Horner's rule with individually rounded operations.  With power != 0 the input is
+ * phase(i) = sum_k coef[k] ((i - i_ref)/rate)^k evaluated in float64 by
+ * Horner's rule with individually rounded operations.  Here i counts samples
+ * on the grid of the whole observation: the first sample of this call is
+ * i_phase (an exact integer, so that the bins do not depend on how a stream
+ * was cut into blocks or shared out over GPUs), and i_ref is the (possibly
+ * fractional) index on that grid at which the polynomial's time is zero.  With power != 0 the input is
  * [n][inner/4][2] complex64 and the four polarization products are formed
  * on the fly.  sum[bin][n_phase][inner] float32 and count[bin][n_phase]
  * int64 are accumulated (+=). */
 int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
-                  int64_t i_first, const int64_t* lo, const int64_t* hi,
+                  int64_t i_first, int64_t i_phase, const int64_t* lo,
+                  const int64_t* hi,
                   int64_t b_first, int64_t n_bins, const int32_t* pbin,
                   const double* coef, int ncoef, double i_ref, double rate,
                   int n_phase, void* sum, void* count, void* stream);

@@ -106,7 +106,7 @@ def test_c3_pfb_dedisperse_power(bt):
     pw = bt.Power(dd)
     want_pfb = orc.pfb(x.astype('f8'), response, ih_samples_per_frame=1 << 16)
     assert pfb.shape == want_pfb.shape
-    assert_voltage(pfb.read(), want_pfb.astype('c8'), tol=2e-5)
+    assert_voltage(pfb.read(), want_pfb.astype('c8'))
     freq = orc.channelize_frequency(800., -1, 2048, rate / 1e6, True, 1)
     op = orc.DispersePlan(-dm, freq, -1, rate / 2048 / 1e6, True,
                           want_pfb.shape[0], pfb.samples_per_frame, (1025, 2),
@@ -115,8 +115,8 @@ def test_c3_pfb_dedisperse_power(bt):
     assert (dd._pad_start, dd._pad_end, dd._ih_samples_per_frame) == (
         op.pad_start, op.pad_end, op.N)
     y = orc.disperse(want_pfb.astype('c8'), op)
-    assert_voltage(dd.read(), y, tol=3e-5)
-    assert_power(pw.read(), orc.power(y, axis=-1), tol=1e-4)
+    assert_voltage(dd.read(), y)
+    assert_power(pw.read(), orc.power(y, axis=-1))
 
 
 def test_c4_frame_full_size(bt):
@@ -150,6 +150,8 @@ def test_c4_frame_full_size(bt):
     other = bt.ArrayStream(x2, t0(bt), rate, frequency=freq, sideband=1)
     d_mix = bt.Dedisperse(mix, dm, samples_per_frame=spf).read(spf)
     d_other = bt.Dedisperse(other, dm, samples_per_frame=spf).read(spf)
+    # (Three results, each within 1e-5 of the oracle, are combined here:
+    # the bound for the combination is (1 + |a| + |b|) 1e-5 = 3.2e-5.)
     assert_voltage(d_mix, a * got[:spf] + b * d_other, tol=2e-5)
     # Energy: the chirp is a pure phase, so a whole frame keeps its power
     # (valid part against the matching part of the circular result).
@@ -158,15 +160,21 @@ def test_c4_frame_full_size(bt):
 
 def test_c5_fold_full_frame(bt):
     """configs[4]: Dedisperse -> Power -> Fold(512, polynomial) over one
-    2^24-point frame: counts bit-exact, sums to 1e-5."""
+    2^24-point frame against the oracle chain (disperse -> power -> fold):
+    counts bit-exact, sums to 1e-5."""
     rate, freq, dm = 512e6, 8192e6, 1000.
     N = 1 << 24
-    spf = N - 1889551 - 2075345
+    pad_start = 1889551
+    spf = N - pad_start - 2075345
     rng = np.random.default_rng(1234572)
     x = cnoise(rng, (N, 2))
     src = bt.ArrayStream(x, t0(bt), rate, frequency=freq, sideband=1,
                          polarization=np.array(['X', 'Y']))
     dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    op = orc.DispersePlan(-dm, freq / 1e6, 1, rate / 1e6, True, N, N, (2,),
+                          samples_per_frame=spf, fast_len=orc.next_pow2)
+    power = orc.power(orc.disperse(x, op), axis=-1)
+    assert power.shape == (spf, 4)
     poly = bt.PolynomialPhase([0.25, 29.946923, -3.77535e-10 / 2.], t0(bt))
     # A pulsar this slow fills 2 of 512 bins in 25 ms: spin it up so that
     # all bins are visited and bin edges are crossed ~10^5 times.
@@ -174,21 +182,18 @@ def test_c5_fold_full_frame(bt):
     for phase in (poly, fast):
         fold = bt.Fold(bt.Power(dd), 512, phase, average=False)
         assert fold._fused == 'power'
+        # Samples are counted on the grid of the source stream: the first
+        # dedispersed sample is its sample pad_start.
+        i_ref, i_0 = phase.grid(fold.ih)
+        assert (i_ref, i_0) == (0., pad_start)
         got = fold.read()
-        dd.seek(0)
-        y = dd.read()
-        power = orc.power(y, axis=-1)
-        i_ref = phase.i_ref(dd.start_time, rate)
-        phases = phase.of_index(np.arange(spf), i_ref, rate)
-        pbin = ((phases % 1.) * 512).astype(int)
-        count = np.bincount(pbin, minlength=512)
-        np.testing.assert_array_equal(got['count'][0, :, 0], count)
-        assert got['count'].sum() == spf * 4
-        for c in range(4):
-            want = np.bincount(pbin, weights=power[:, c].astype('f8'),
-                               minlength=512)
-            np.testing.assert_allclose(got['data'][0, :, c], want, rtol=2e-5,
-                                       atol=2e-5 * np.abs(want).max())
+        want, wcount = orc.fold(      # sums in float64
+            power.astype('f8'), np.array([0, spf]), 512,
+            lambda i: phase.of_index(i + i_0, i_ref, rate))
+        np.testing.assert_array_equal(got['count'],
+                                      np.broadcast_to(wcount, got.shape))
+        assert got['count'][..., 0].sum() == spf
+        assert_power(got['data'], want.astype('f4'))
 
 
 def test_empty_and_edge_reads(bt):

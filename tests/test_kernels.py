@@ -440,7 +440,7 @@ def test_fold(backend, power, n_phase, n_tbin):
     for i0, i1 in ((0, split), (split, n)):
         ptr = ctypes.c_void_p(backend.ptr(d_in).value + i0 * item)
         backend.lib.check(backend.lib.bbt_fold_exec(
-            ptr, power, i1 - i0, inner, i0, backend.ptr(d_lo),
+            ptr, power, i1 - i0, inner, i0, i0, backend.ptr(d_lo),
             backend.ptr(d_hi), 0, n_tbin, None,
             coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(coef),
             i_ref, rate, n_phase, backend.ptr(d_sum), backend.ptr(d_cnt),
@@ -455,13 +455,17 @@ def test_fold(backend, power, n_phase, n_tbin):
     assert_power(backend.to_host(d_sum), want)
 
 
-@pytest.mark.parametrize('rate,coef,i_first', [
-    (512e6, [0.1, 641.234567, -1.5e-3], 0),
-    (1e6 / 3 + 0.123, [-5.3, -77.7, 0.01, 1e-4, -2e-6, 3e-8], 10 ** 12),
-    (float(np.nextafter(8e6, 0)), [1e5 + 0.7, 200.25], 123456789),
-    (33554432., [0., 1000.], 0),
+@pytest.mark.parametrize('rate,coef,i_first,i_block', [
+    (512e6, [0.1, 641.234567, -1.5e-3], 0, 0),
+    (1e6 / 3 + 0.123, [-5.3, -77.7, 0.01, 1e-4, -2e-6, 3e-8], 10 ** 12, 0),
+    (float(np.nextafter(8e6, 0)), [1e5 + 0.7, 200.25], 123456789, 0),
+    (33554432., [0., 1000.], 0, 0),
+    # A block cut out of a longer stream: samples are numbered from the
+    # block's start for the time bins and on the whole stream's grid for
+    # the phases.
+    (512e6, [0.1, 641.234567, -1.5e-3], 7 * 12812320 + 1889551, 7 * 12812320),
 ])
-def test_fold_phase_bins_exact(backend, rate, coef, i_first):
+def test_fold_phase_bins_exact(backend, rate, coef, i_first, i_block):
     """Phase bins are bit-exact with the float64 evaluation of the oracle for
     awkward rates, long polynomials, negative phases and large sample
     indices (the kernel divides through a reciprocal and pads the Horner
@@ -477,15 +481,15 @@ def test_fold_phase_bins_exact(backend, rate, coef, i_first):
     want_cnt = np.bincount(pbin, minlength=n_phase)
     want = np.zeros((n_phase, 4))
     np.add.at(want, pbin, x.astype('f8'))
-    lo = np.array([i_first], dtype=np.int64)
-    hi = np.array([i_first + n], dtype=np.int64)
+    lo = np.array([i_first - i_block], dtype=np.int64)
+    hi = np.array([i_first - i_block + n], dtype=np.int64)
     d_in = backend.to_dev(x)
     d_lo, d_hi = backend.to_dev(lo), backend.to_dev(hi)
     d_sum = backend.zeros((1, n_phase, 4), 'f4')
     d_cnt = backend.zeros((1, n_phase), 'i8')
     backend.lib.check(backend.lib.bbt_fold_exec(
-        backend.ptr(d_in), 0, n, 4, i_first, backend.ptr(d_lo),
-        backend.ptr(d_hi), 0, 1, None,
+        backend.ptr(d_in), 0, n, 4, i_first - i_block, i_first,
+        backend.ptr(d_lo), backend.ptr(d_hi), 0, 1, None,
         coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(coef),
         i_ref, rate, n_phase, backend.ptr(d_sum), backend.ptr(d_cnt),
         backend.stream))

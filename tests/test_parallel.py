@@ -63,6 +63,8 @@ def _worker(rank, world, port, out_dir):
     block, f0, f1 = parallel.shard_frames(src, SPF, pad, rank, world)
     dd, fold = _chain(bt, block, src.start_time)
     assert dd.shape[0] == (f1 - f0) * SPF
+    # The block's samples are numbered on the grid of the whole stream.
+    assert fold.phase.grid(fold.ih) == (0., f0 * SPF + dd._pad_start)
     assert abs((dd.start_time - probe.start_time) - f0 * SPF / RATE) < 1e-12
     sums, counts = fold.read_sums()
     local = (sums.clone().numpy(), counts.clone().numpy())
@@ -110,13 +112,14 @@ def test_fold_sharded_over_two_ranks(tmp_path):
     y = orc.disperse(x, op)[:n_out]
     power = orc.power(y, axis=-1)
     poly = fold.phase
-    i_ref = poly.i_ref(pw.start_time, RATE)
+    # Phases count samples on the grid of the source stream, whatever block
+    # a rank was given: bins are bit-exact under sharding.
+    i_ref, i_0 = poly.grid(pw)
+    assert i_0 == dd._pad_start and i_ref == 0.
     want, wcount = orc.fold(power, np.array([0, n_out]), N_PHASE,
-                            lambda i: poly.of_index(i, i_ref, RATE))
+                            lambda i: poly.of_index(i + i_0, i_ref, RATE))
     got_cnt = r[0]['counts'].reshape(wcount.shape[:2])
-    # Bin edges: the sharded ranks evaluate the polynomial from their own
-    # block start; allow the (rare) sample exactly on an edge to differ.
-    assert np.abs(got_cnt - wcount[..., 0]).sum() <= 2
+    np.testing.assert_array_equal(got_cnt, wcount[..., 0])
     np.testing.assert_allclose(r[0]['sums'].reshape(want.shape), want,
                                rtol=1e-5, atol=1e-5 * np.abs(want).max())
     with np.errstate(invalid='ignore'):
