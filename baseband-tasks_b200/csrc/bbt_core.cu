@@ -85,10 +85,15 @@ cf* make_roots(int64_t count, double denom) {
   }
   void* dev = nullptr;
   if (dev_alloc(&dev, count * sizeof(cf))) return nullptr;
-  if (h2d(dev, host.data(), count * sizeof(cf), 0)) return nullptr;
+  bool ok = !h2d(dev, host.data(), count * sizeof(cf), 0);
 #if !defined(BBT_EMULATE)
-  cudaStreamSynchronize(0);  // host vector goes out of scope
+  // The host vector goes out of scope: wait for the copy.
+  if (ok && cudaStreamSynchronize(0) != cudaSuccess) ok = false;
 #endif
+  if (!ok) {
+    dev_free(dev);
+    return nullptr;
+  }
   return static_cast<cf*>(dev);
 }
 
@@ -101,9 +106,40 @@ const cf* twiddle_table(int log2n) {
   if (it != tables.end()) return it->second;
   const int64_t n = int64_t(1) << log2n;
   cf* t = make_roots(n, (double)n);
-  tables[key] = t;
+  if (t) tables[key] = t;  // a failed allocation is retried next time
   return t;
 }
+
+#if !defined(BBT_EMULATE)
+int sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> counts;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = counts.find(dev);
+  if (it != counts.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  counts[dev] = n;
+  return n;
+}
+
+// cudaFuncSetAttribute once per (device, kernel) and size increase instead of
+// on every launch.
+int set_max_smem(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  const std::pair<int, const void*> key(current_device(), kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return 0;
+  const int rc = (int)cudaFuncSetAttribute(
+      kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (!rc) done[key] = bytes;
+  return rc;
+}
+#endif
 
 namespace {
 BBT_GLOBAL void strided_copy_kernel(const float4* in, float4* out,

@@ -212,6 +212,9 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
         h2d(dfreq, freq_mhz, n_chirp * sizeof(double), 0) ||
         h2d(dref, fref_mhz, n_chirp * sizeof(double), 0) ||
         h2d(dsb, sideband, n_chirp, 0)) {
+      if (dfreq) dev_free(dfreq);
+      if (dref) dev_free(dref);
+      if (dsb) dev_free(dsb);
       bbt_dedisperse_plan_destroy(p);
       return fail(BBT_ENOMEM, "cannot stage chirp parameters");
     }
@@ -297,14 +300,46 @@ int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* p,
   return n_frames * p->n * p->n_series * (int64_t)sizeof(cf);
 }
 
+}  // extern "C"
+
+// Frames per launch: the column kernels put the frame in grid.y.
+static const int64_t kMaxFramesPerLaunch = 65535;
+
+static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
+                               int64_t in_frame_stride, int64_t n_frames,
+                               int64_t skip, void* out,
+                               int64_t out_frame_stride, void* work,
+                               void* stream);
+
+extern "C" {
+
 int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
                         int64_t in_frame_stride, int64_t n_frames,
                         int64_t skip, void* out, int64_t out_frame_stride,
                         void* work, void* stream) {
   if (!p || !in || !out) return fail(BBT_EINVAL, "null argument");
   if (n_frames <= 0) return BBT_OK;
-  if (n_frames > 65535) return fail(BBT_EUNSUPPORTED, "too many frames per call");
   if (skip < 0 || skip >= p->n_valid) return fail(BBT_EINVAL, "bad skip");
+  // Long runs of short frames go in several launches (same stream, so the
+  // work buffer of the first part is free again when the next one starts).
+  for (int64_t f0 = 0; f0 < n_frames; f0 += kMaxFramesPerLaunch) {
+    const int64_t nf = std::min(kMaxFramesPerLaunch, n_frames - f0);
+    const int rc = dedisperse_exec_run(
+        p, static_cast<const cf*>(in) + f0 * in_frame_stride, in_frame_stride,
+        nf, skip, static_cast<cf*>(out) + f0 * out_frame_stride,
+        out_frame_stride, work, stream);
+    if (rc) return rc;
+  }
+  return BBT_OK;
+}
+
+}  // extern "C"
+
+static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
+                               int64_t in_frame_stride, int64_t n_frames,
+                               int64_t skip, void* out,
+                               int64_t out_frame_stride, void* work,
+                               void* stream) {
   bbt_stream_t st = as_stream(stream);
   DdArgs a;
   a.in = static_cast<const cf*>(in);
@@ -365,6 +400,8 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
 #undef F
   return rc;
 }
+
+extern "C" {
 
 int bbt_dedisperse_plan_destroy(bbt_dedisperse_plan* p) {
   if (!p) return BBT_OK;

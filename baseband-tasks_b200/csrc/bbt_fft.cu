@@ -134,12 +134,17 @@ int bbt_fft_exec(const bbt_fft_plan* p, const void* in, void* out, void* work,
   if ((rc = check_launch("twiddle kernel"))) return rc;
   FftArgs row{w, w, p->tw, p->outer * n1, 1, inverse, p->scale};
   if ((rc = run_fft(p->log2n2, BBT_C2C, row, st))) return rc;
-  // w[k1][k2] -> out[k2][k1]  (bin k = k1 + n1*k2)
-  dim3 grid((unsigned)ceil_div(n2, 32), (unsigned)ceil_div(n1, 32),
-            (unsigned)p->outer);
-  BBT_LAUNCH(transpose_kernel, grid, dim3(32, 8), 32 * 33 * sizeof(cf), st, w,
-             static_cast<cf*>(out), n1, n2);
-  return check_launch("transpose kernel");
+  // w[k1][k2] -> out[k2][k1]  (bin k = k1 + n1*k2); the batch goes in grid.z,
+  // at most 65535 at a time.
+  for (int64_t b0 = 0; b0 < p->outer; b0 += 65535) {
+    const int64_t nb = std::min<int64_t>(65535, p->outer - b0);
+    dim3 grid((unsigned)ceil_div(n2, 32), (unsigned)ceil_div(n1, 32),
+              (unsigned)nb);
+    BBT_LAUNCH(transpose_kernel, grid, dim3(32, 8), 32 * 33 * sizeof(cf), st,
+               w + b0 * p->n, static_cast<cf*>(out) + b0 * p->n, n1, n2);
+    if ((rc = check_launch("transpose kernel"))) return rc;
+  }
+  return BBT_OK;
 }
 
 int bbt_fft_plan_destroy(bbt_fft_plan* p) {

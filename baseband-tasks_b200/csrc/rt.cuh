@@ -110,11 +110,8 @@ inline int sm_count() { return 4; }
     bbt::ProfScope bbt_prof_scope(#kernel, stream);          \
     kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);      \
   } while (0)
-#define BBT_SET_SMEM(kernel, bytes)                                         \
-  ((bytes) > 48 * 1024                                                      \
-       ? (int)cudaFuncSetAttribute(                                         \
-             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)) \
-       : 0)
+#define BBT_SET_SMEM(kernel, bytes) \
+  bbt::set_max_smem(reinterpret_cast<const void*>(kernel), (bytes))
 typedef cudaStream_t bbt_stream_t;
 extern __shared__ float4 bbt_dyn_smem[];
 namespace bbt {
@@ -169,11 +166,7 @@ inline const char* launch_error() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
-inline int sm_count() {
-  int dev = 0, n = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess)
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n;
-}
+int sm_count();  // cached per device (bbt_core.cu)
+int set_max_smem(const void* kernel, size_t bytes);
 }  // namespace bbt
 #endif

@@ -242,11 +242,13 @@ class Disperse(PaddedTaskBase):
         S, spf = self._n_series, self.samples_per_frame
         N = self._ih_samples_per_frame
         assert x.shape[0] == (n_frames - 1) * spf + N
-        result = out
-        if result is None:
-            result = B.empty((n_frames * spf,) + self.sample_shape,
-                             np.complex64)
-        assert result.is_contiguous() and result.shape[0] == n_frames * spf
+        # The kernels write complex64: a caller's buffer of another dtype
+        # (a complex128 stream) or layout is filled through a temporary.
+        direct = (out is not None and out.is_contiguous()
+                  and out.dtype == B.torch_dtype(np.complex64))
+        result = out if direct else B.empty(
+            (n_frames * spf,) + self.sample_shape, np.complex64)
+        assert result.shape[0] == n_frames * spf
         wb = lib.bbt_dedisperse_work_bytes(plan, n_frames)
         if self._work is None or self._work.numel() < wb:
             self._work = None
@@ -254,6 +256,9 @@ class Disperse(PaddedTaskBase):
         lib.check(lib.bbt_dedisperse_exec(
             plan, B.ptr(x), spf * S, n_frames, 0, B.ptr(result), spf * S,
             B.ptr(self._work), _cabi.stream_ptr()))
+        if out is not None and not direct:
+            out.copy_(result)
+            return out
         return result
 
     def _task_frames_real(self, data, n_frames, out, host):

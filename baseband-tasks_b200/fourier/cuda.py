@@ -36,6 +36,8 @@ class CudaFFTBase(FFTBase):
     def __init__(self, direction='forward'):
         super().__init__(direction=direction)
         self._plan = None
+        self._work = None
+        self._work_bytes = 0
         shape, axis = self._time_shape, self._axis % len(self._time_shape)
         self._n = shape[axis]
         self._outer = int(np.prod(shape[:axis], dtype=np.int64))
@@ -77,6 +79,14 @@ class CudaFFTBase(FFTBase):
             self._work_bytes = lib.bbt_fft_plan_work_bytes(plan)
         return self._plan
 
+    def _get_work(self):
+        """Scratch of the large transforms, allocated once per FFT object."""
+        if not self._work_bytes:
+            return None
+        if self._work is None or self._work.device != _cabi.device():
+            self._work = B.empty((self._work_bytes,), np.uint8)
+        return self._work
+
     def __call__(self, a, out=None):
         """Transform ``a``; ``out`` may name a device tensor to fill."""
         return self._fft(a, out=out)
@@ -103,14 +113,12 @@ class CudaFFTBase(FFTBase):
               and out.dtype == B.torch_dtype(single_out)
               and out.numel() == int(np.prod(self._out_shape, dtype=np.int64))):
             lib.check(lib.bbt_fft_exec(
-                plan, B.ptr(x), B.ptr(out),
-                B.ptr(B.empty((self._work_bytes,), np.uint8)
-                      if self._work_bytes else None), _cabi.stream_ptr()))
+                plan, B.ptr(x), B.ptr(out), B.ptr(self._get_work()),
+                _cabi.stream_ptr()))
             return out
         else:
             out = B.empty(self._out_shape, single_out)
-        work = (B.empty((self._work_bytes,), np.uint8)
-                if self._work_bytes else None)
+        work = self._get_work()
         lib.check(lib.bbt_fft_exec(plan, B.ptr(x), B.ptr(out), B.ptr(work),
                                    _cabi.stream_ptr()))
         if self._transpose:

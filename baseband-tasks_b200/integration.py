@@ -181,7 +181,8 @@ class Integrate(BaseTaskBase):
         self._src_ratio = 1      # source samples per ih sample
         if (type(ih) is Power and type(getattr(ih, 'ih', None)) is Channelize
                 and np.dtype(ih.ih.ih.dtype) == np.complex64
-                and ih._axis == ih.ndim - 1 and ih.ih.ih.ndim >= 2):
+                and ih._axis == ih.ndim - 1 and ih.ih.ih.ndim >= 2
+                and _fusable_channelizer(ih.ih._n)):
             ch = ih.ih
             self._fused = 'chanpow'
             self._src = ch.ih
@@ -389,6 +390,12 @@ class Integrate(BaseTaskBase):
                         int(self._average_in_kernel), _cabi.stream_ptr()))
             pos = nxt
         assert n_bins == count.shape[0]
+
+
+def _fusable_channelizer(n):
+    """Lengths the fused Channelize -> Power -> Integrate kernel takes (one
+    spectrum per block FFT); longer ones are read unfused through `ih`."""
+    return 2 <= n <= 16384 and n & (n - 1) == 0
 
 
 def _as_dtype(t, dtype):

@@ -871,3 +871,66 @@ def test_payload_stream(bt, bps, complex_data):
     assert_power(sq.read(), orc.square(want.astype(fh.dtype)))
     with pytest.raises(NotImplementedError):
         bt.PayloadStream(words, 3, shape, start_time(bt), 1e6)
+
+
+# ------------------------------------------------- round-1 advisor findings
+def test_dedisperse_complex128_stream(bt):
+    """A complex128 stream: aligned, unaligned and multi-block reads all give
+    the complex64 result (the kernels write complex64; the caller's complex128
+    buffer is filled through a temporary)."""
+    rng = np.random.default_rng(40)
+    x = cnoise(rng, (5 * 4096, 2))
+    kw = dict(frequency=300e6, sideband=1)
+    s16 = bt.ArrayStream(x.astype('c16'), start_time(bt), 1e6,
+                         samples_per_frame=1000, **kw)
+    s8 = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=1000, **kw)
+    spf = 4096 - 923
+    d16 = bt.Dedisperse(s16, 3., samples_per_frame=spf)
+    d8 = bt.Dedisperse(s8, 3., samples_per_frame=spf)
+    want = d8.read()
+    got = d16.read()
+    assert got.dtype == np.complex128
+    np.testing.assert_array_equal(got.astype('c8'), want)
+    d16.seek(37)
+    part = d16.read(2 * spf + 11)       # unaligned start, several frames
+    np.testing.assert_array_equal(part.astype('c8'), want[37:37 + 2 * spf + 11])
+    op = orc.DispersePlan(-3., 300., 1, 1., True, x.shape[0], 1000, (2,),
+                          samples_per_frame=spf, fast_len=orc.next_pow2)
+    assert_voltage(got.astype('c8'), orc.disperse(x, op))
+
+
+def test_dedisperse_many_short_frames(bt, monkeypatch):
+    """More frames in one read than a single launch takes (65535)."""
+    n_frames = 70000
+    N, spf = 16, 14                 # pads 1 + 1
+    n = (n_frames - 1) * spf + N
+    rng = np.random.default_rng(41)
+    x = cnoise(rng, (n,))
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=n,
+                         frequency=300e6, sideband=1)
+    dd = bt.Dedisperse(src, 0.0045, samples_per_frame=spf)
+    assert (dd._ih_samples_per_frame, dd._pad_start, dd._pad_end) == (N, 1, 1)
+    got = dd.read()
+    assert got.shape == (n_frames * spf,)
+    op = orc.DispersePlan(-0.0045, 300., 1, 1., True, n, n, (),
+                          samples_per_frame=spf, fast_len=orc.next_pow2)
+    assert (op.pad_start, op.pad_end, op.N) == (1, 1, N)
+    assert_voltage(got, orc.disperse(x, op))
+
+
+def test_integrate_long_channelizer_unfused(bt):
+    """Channelizers longer than the fused kernel takes are read unfused."""
+    n_chan = 32768
+    rng = np.random.default_rng(42)
+    x = cnoise(rng, (3 * n_chan, 2))
+    src = bt.ArrayStream(x, start_time(bt), 1e6, samples_per_frame=n_chan,
+                         polarization=np.array(['X', 'Y']))
+    it = bt.Integrate(bt.Power(bt.Channelize(src, n_chan)), 3, average=False)
+    assert it._fused is None
+    short = bt.Integrate(bt.Power(bt.Channelize(src, 1024)), 3)
+    assert short._fused == 'chanpow'
+    got = it.read()
+    power = orc.power(orc.channelize(x, n_chan), axis=-1)
+    want, count = orc.integrate(power, np.array([0, 3]))
+    assert np.all(got['count'] == 3)
+    assert_power(got['data'], want)
