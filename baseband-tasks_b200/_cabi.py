@@ -71,6 +71,7 @@ _SIGNATURES = {
     'bbt_average_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int64, c_void_p]),
     'bbt_launch_count': (c_int64, []),
+    'bbt_tune_set': (c_int, [ctypes.c_char_p, c_int]),
     'bbt_profile_enable': (c_int, [c_int]),
     'bbt_profile_report': (c_int, [ctypes.c_char_p, c_int64]),
     'bbt_strided_copy_bench': (c_int, [c_void_p, c_void_p, c_int64, c_int64,

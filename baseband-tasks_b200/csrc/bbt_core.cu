@@ -1,9 +1,12 @@
 // C-ABI implementation (see include/bbt_b200.h): errors, twiddle tables,
 // launch counting / profiling and the measurement helper.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace bbt {
 
@@ -110,6 +113,100 @@ const cf* twiddle_table(int log2n) {
   return t;
 }
 
+// ------------------------------------------------------------ tuning knobs
+// Kernel variants are chosen by the library; for A/B measurements a variant
+// can be forced with bbt_tune_set("key", value) or the environment variable
+// BBT_TUNE="key=value,key=value".
+namespace {
+std::mutex g_tune_mu;
+std::map<std::string, int> g_tune;
+bool g_tune_env_read = false;
+}  // namespace
+int tune(const char* key, int dflt) {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  if (!g_tune_env_read) {
+    g_tune_env_read = true;
+    const char* env = getenv("BBT_TUNE");
+    if (env) {
+      std::string text(env);
+      size_t pos = 0;
+      while (pos < text.size()) {
+        size_t end = text.find(',', pos);
+        if (end == std::string::npos) end = text.size();
+        const std::string item = text.substr(pos, end - pos);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos && !g_tune.count(item.substr(0, eq)))
+          g_tune[item.substr(0, eq)] = atoi(item.c_str() + eq + 1);
+        pos = end + 1;
+      }
+    }
+  }
+  auto it = g_tune.find(key);
+  return it == g_tune.end() ? dflt : it->second;
+}
+void tune_set(const char* key, int value) {
+  std::lock_guard<std::mutex> lock(g_tune_mu);
+  g_tune[key] = value;
+}
+
+// ------------------------------------------------------------- tensor maps
+#if defined(BBT_EMULATE)
+int make_tensor_map(TensorMap* map, void* base, int elem_bytes, int rank,
+                    const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  if (rank < 1 || rank > 3) return -1;
+  map->base = static_cast<char*>(base);
+  map->rank = rank;
+  for (int i = 0; i < 3; ++i) {
+    map->dim[i] = i < rank ? dims[i] : 1;
+    map->stride[i] = i == 0 ? (uint64_t)elem_bytes
+                            : (i < rank ? strides_bytes[i] : 0);
+    map->box[i] = i < rank ? box[i] : 1;
+  }
+  return 0;
+}
+#else
+int make_tensor_map(TensorMap* map, void* base, int elem_bytes, int rank,
+                    const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  // The driver entry point is looked up through the runtime, so the library
+  // does not link against libcuda (and loads on machines without a driver).
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
+                             void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*,
+                             CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn,
+                                  cudaEnableDefault, &q) != cudaSuccess ||
+          !fn)
+        return -1;
+      encode = reinterpret_cast<Encode>(fn);
+    }
+  }
+  if (rank < 1 || rank > 3) return -1;
+  cuuint64_t d[3], s[2];
+  cuuint32_t b[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) d[i] = dims[i], b[i] = box[i];
+  for (int i = 1; i < rank; ++i) s[i - 1] = strides_bytes[i];
+  const CUtensorMapDataType dt =
+      elem_bytes == 8   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+      : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                        : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const CUresult r =
+      encode(map, dt, rank, base, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+#endif
+
 #if !defined(BBT_EMULATE)
 int sm_count() {
   static std::mutex mu;
@@ -163,7 +260,13 @@ using namespace bbt;
 
 extern "C" {
 
-int bbt_version(void) { return 101; }
+int bbt_version(void) { return 200; }
+
+int bbt_tune_set(const char* key, int value) {
+  if (!key) return fail(BBT_EINVAL, "null key");
+  tune_set(key, value);
+  return BBT_OK;
+}
 
 const char* bbt_last_error(void) { return last_error().c_str(); }
 

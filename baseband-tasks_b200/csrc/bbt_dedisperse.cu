@@ -1,6 +1,7 @@
 // C-ABI implementation (see include/bbt_b200.h): coherent (de)dispersion.
 #include "common.cuh"
 #include "kernels_dedisperse.cuh"
+#include "tma.cuh"
 
 using namespace bbt;
 
@@ -9,6 +10,8 @@ struct bbt_dedisperse_plan {
   int log2n, log2n1, log2n2;
   int planar;      // work-buffer layout of the three-pass split
   int half;        // 256-thread CTAs, half-size tiles
+  int row2;        // row pass by dd_row2_kernel (chirp rows in its order)
+  const cf* tw_sub;  // roots of unity for its sub-transforms (n2 / 32)
   const cf* tw1;   // roots of unity for the column FFTs (n1)
   const cf* tw2;   // for the row FFTs (n2), or the whole single-pass frame
   cf* big_lo;
@@ -35,6 +38,69 @@ int col_lanes(int l1) {
   return kColThreads >> (l1 - log2e);
 }
 
+// Column passes through tensor-map bulk copies; BBT_EUNSUPPORTED (without
+// touching the error message) when the geometry does not fit a tensor map.
+template <class C>
+int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
+                      bbt_stream_t st) {
+  const int64_t N2 = a.N >> a.log2n1, S = a.S, n2s = N2 * S;
+  const bool planar_src = inverse && a.planar;
+  if (C::G > 256 || n2s < C::G || (n2s & 1)) return BBT_EUNSUPPORTED;
+  DdColTma m;
+  m.box_rows = C::N < 256 ? C::N : 256;
+  m.n_boxes = C::N / m.box_rows;
+  m.tn = 1;
+  TensorMap map;
+  uint64_t dims[3], strides[3];
+  uint32_t box[3];
+  void* base;
+  if (planar_src) {
+    if (S > C::G || C::G % S || ((C::G / S) & 1) || N2 < C::G / S)
+      return BBT_EUNSUPPORTED;
+    m.tn = (int)(C::G / S);
+    base = a.work;
+    dims[0] = N2, dims[1] = S, dims[2] = n_frames * C::N;
+    strides[0] = 8, strides[1] = N2 * 8, strides[2] = S * N2 * 8;
+    box[0] = m.tn, box[1] = (uint32_t)S, box[2] = m.box_rows;
+  } else {
+    const int64_t frame_stride = inverse ? a.N * a.S : a.in_frame_stride;
+    if (frame_stride & 1) return BBT_EUNSUPPORTED;
+    base = inverse ? static_cast<void*>(a.work)
+                   : const_cast<void*>(static_cast<const void*>(a.in));
+    dims[0] = n2s, dims[1] = C::N, dims[2] = n_frames;
+    strides[0] = 8, strides[1] = n2s * 8, strides[2] = frame_stride * 8;
+    box[0] = C::G, box[1] = m.box_rows, box[2] = 1;
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) return BBT_EUNSUPPORTED;
+  if (make_tensor_map(&map, base, 8, 3, dims, strides, box))
+    return BBT_EUNSUPPORTED;
+  constexpr size_t kTile = (size_t)C::N * C::G * sizeof(cf);
+  const size_t smem =
+      (C::SMEM_BYTES > kTile ? C::SMEM_BYTES : kTile) + sizeof(Mbar);
+  const int64_t tiles = ceil_div(n2s, C::G) * n_frames;
+  const int per_sm = C::THREADS <= 256 ? 2 : 1;
+  const int64_t ctas = std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
+  int rc;
+  if (inverse) {
+    auto kern = dd_col_tma_kernel<C, true>;
+    if (BBT_SET_SMEM(kern, smem))
+      return fail(BBT_ECUDA, "cannot set shared memory size");
+    prof_next_name = "dd_col_inv";
+    BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a, m,
+               map);
+    rc = check_launch("dedispersion column kernel");
+  } else {
+    auto kern = dd_col_tma_kernel<C, false>;
+    if (BBT_SET_SMEM(kern, smem))
+      return fail(BBT_ECUDA, "cannot set shared memory size");
+    prof_next_name = "dd_col_fwd";
+    BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a, m,
+               map);
+    rc = check_launch("dedispersion column kernel");
+  }
+  return rc;
+}
+
 template <int L1, bool HALF = false>
 int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
                   bbt_stream_t st) {
@@ -42,6 +108,10 @@ int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
   DdArgs a = a0;
   if (HALF) a.ahead *= 2;
   const int64_t cols = (a.N >> L1) * a.S;
+  if (tune("col_tma", 1)) {
+    const int rc = launch_dd_col_tma<C>(inverse, a, n_frames, st);
+    if (rc != BBT_EUNSUPPORTED) return rc;  // else: the per-thread-load kernels
+  }
   dim3 grid((unsigned)ceil_div(cols, C::G), (unsigned)n_frames);
   const size_t smem = C::SMEM_BYTES;
   auto kern = inverse ? dd_col_inv_kernel<C> : dd_col_fwd_kernel<C>;
@@ -74,6 +144,35 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   }
   if (blocks * n_frames > 2147483647LL)
     return fail(BBT_EUNSUPPORTED, "grid too large");
+  if constexpr (PLANAR && !HALF && L2 >= 11) {
+    if (a.tw_sub) {   // the plan stored its chirp for dd_row2_kernel
+      if (reinterpret_cast<uintptr_t>(a.work) & 15)
+        return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
+      const size_t smem = Row2Cfg<C>::kSmemBytes;
+      auto kern = dd_row2_kernel<C>;
+      if (BBT_SET_SMEM(kern, smem))
+        return fail(BBT_ECUDA, "cannot set shared memory size");
+      const int64_t ctas =
+          std::min<int64_t>(blocks * n_frames, (int64_t)sm_count());
+      prof_next_name = "dd_row";
+      BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a);
+      return check_launch("dedispersion row kernel");
+    }
+  }
+  if constexpr (PLANAR && !HALF) {
+    // Persistent CTAs fed by bulk copies (one tile = one contiguous range).
+    if (tune("row_tma", 1) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
+      const size_t smem = C::SMEM_BYTES + sizeof(Mbar);
+      auto kern = dd_row_tma_kernel<C>;
+      if (BBT_SET_SMEM(kern, smem))
+        return fail(BBT_ECUDA, "cannot set shared memory size");
+      const int64_t ctas =
+          std::min<int64_t>(blocks * n_frames, (int64_t)sm_count());
+      prof_next_name = "dd_row";
+      BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a);
+      return check_launch("dedispersion row kernel");
+    }
+  }
   dim3 grid((unsigned)(blocks * n_frames));
   const size_t smem = C::SMEM_BYTES;
   auto kern = dd_row_kernel<C, PLANAR>;
@@ -181,6 +280,11 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     // faster than one 128 KB tile); bit 14 of the hint switches that off.
     if (!planar && !((hint >> 14) & 1)) p->half |= 2;
   }
+  // Long contiguous rows: the formulation with warp-local sub-transforms.
+  p->row2 = p->log2n1 > 0 && p->planar && p->log2n2 >= 11 && !(p->half & 2) &&
+            tune("row2", 1);
+  p->tw_sub = p->row2 ? twiddle_table(p->log2n2 - 5) : nullptr;
+  if (p->row2 && !p->tw_sub) p->row2 = 0;
   p->tw2 = twiddle_table(p->log2n2);
   p->tw1 = p->log2n1 > 0 ? twiddle_table(p->log2n1) : p->tw2;
   void* d = nullptr;
@@ -219,6 +323,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
       return fail(BBT_ENOMEM, "cannot stage chirp parameters");
     }
     ChirpArgs ca;
+    ca.row2_log2n2 = p->row2 ? p->log2n2 : 0;
     ca.chirp = p->chirp;
     ca.freq_mhz = static_cast<const double*>(dfreq);
     ca.fref_mhz = static_cast<const double*>(dref);
@@ -263,7 +368,8 @@ int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* p,
         (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
     BBT_LAUNCH(chirp_scatter_kernel, dim3(blocks), dim3(256), 0,
                (bbt_stream_t)0, p->chirp, static_cast<const cf*>(tmp), p->n,
-               int64_t(1) << p->log2n1, p->n_chirp);
+               int64_t(1) << p->log2n1, p->n_chirp,
+               p->row2 ? p->log2n2 : 0);
     rc = check_launch("response scatter kernel");
 #if !defined(BBT_EMULATE)
     if (!rc && cudaStreamSynchronize(0) != cudaSuccess)
@@ -290,7 +396,9 @@ int bbt_dedisperse_plan_get_response(const bbt_dedisperse_plan* p,
   for (int64_t c = 0; c < p->n_chirp; ++c)
     for (int64_t k1 = 0; k1 < n1; ++k1)
       for (int64_t k2 = 0; k2 < n2; ++k2)
-        out[c * p->n + k1 + n1 * k2] = tmp[c * p->n + k1 * n2 + k2];
+        out[c * p->n + k1 + n1 * k2] =
+            tmp[c * p->n + k1 * n2 +
+                (p->row2 ? row2_pos(k2, p->log2n2) : k2)];
   return BBT_OK;
 }
 
@@ -347,6 +455,7 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.work = static_cast<cf*>(work);
   a.tw = p->tw2;
   a.tw1 = p->tw1;
+  a.tw_sub = p->tw_sub;
   a.big = BigTwiddle{p->big_lo, p->big_hi};
   a.chirp = p->chirp;
   a.series_map = p->series_map;

@@ -54,6 +54,9 @@ int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
     if (!INTEGRATE)
       return launch_chanpow_cfg<FftCfg<10, 5, 512>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
+    if (tune("chanpow_e16", 0))   // 16 values per thread, twice the warps
+      return launch_chanpow_cfg<FftCfg<10, 4, 512>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
     return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
                                                              max_width, st);
   }
@@ -74,6 +77,20 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
   a.msub = msub;
   const int64_t blocks = ceil_div(msub * a.M, units);
   dim3 grid((unsigned)blocks, (unsigned)(INTEGRATE ? n_bins : 1));
+  if constexpr (INTEGRATE && units >= 1 &&
+                ChanPowTma<C>::smem_bytes(1) <= 220 * 1024) {
+    // Narrow samples: whole tiles by bulk copies (chanpow_tma_kernel).
+    if (a.M <= units && units % a.M == 0 &&
+        !(reinterpret_cast<uintptr_t>(a.in) & 15) && tune("chanpow_tma", 1)) {
+      const size_t smem = ChanPowTma<C>::smem_bytes(a.M);
+      auto kern = chanpow_tma_kernel<C>;
+      if (BBT_SET_SMEM(kern, smem))
+        return fail(BBT_ECUDA, "cannot set shared memory size");
+      prof_next_name = "chanpow_integrate";
+      BBT_LAUNCH(kern, grid, dim3(C::THREADS), smem, st, a);
+      return check_launch("channelize-power kernel");
+    }
+  }
   // A second tile for asynchronous staging where it fits (see the kernel).
   const bool stage =
       INTEGRATE && C::SMEM_BYTES + (size_t)C::G * C::N * sizeof(cf) <= 200 * 1024;

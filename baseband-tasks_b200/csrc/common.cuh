@@ -32,6 +32,10 @@ cf* make_roots(int64_t count, double denom);
 // Per-device table of the 2^log2n-th roots of unity, exp(-2 pi i m / 2^log2n).
 const cf* twiddle_table(int log2n);
 
+// Tuning knob ``key`` (bbt_tune_set / BBT_TUNE), or ``dflt`` if not set.
+int tune(const char* key, int dflt);
+void tune_set(const char* key, int value);
+
 inline unsigned grid_for(int64_t total, int threads) {
   return (unsigned)std::max<int64_t>(
       1, std::min<int64_t>(ceil_div(total, threads), (int64_t)sm_count() * 16));

@@ -344,6 +344,21 @@ struct FftCfg {
       Plan::NS > 1 ? (size_t)G * NPAD * sizeof(float) * 2 : 16;
 };
 
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+#define BBT_SYNC() __syncthreads()
+#define BBT_SYNCWARP() __syncwarp()
+#elif defined(BBT_EMULATE)
+}  // namespace bbt
+void bbt_emu_syncthreads();
+void bbt_emu_syncwarp();
+namespace bbt {
+#define BBT_SYNC() bbt_emu_syncthreads()
+#define BBT_SYNCWARP() bbt_emu_syncwarp()
+#else
+#define BBT_SYNC()
+#define BBT_SYNCWARP()
+#endif
+
 // Exchange-buffer addressing.  G FFTs ("lanes") share one CTA.
 //  LaneFast: consecutive threads work on consecutive lanes (column tiles);
 //  slot = padslot(p) * G + g.
@@ -352,6 +367,8 @@ struct FftCfg {
 // ``slot(p)`` is the padded position of element p; ``ref(s)`` the storage
 // of padded position s.  Offsets between the elements a thread touches in one
 // stage are compile-time constants in padded positions (see fft_stage).
+// ``sync()`` is the barrier between the writes and the reads of an exchange:
+// the whole CTA, or only the warp when all threads of a transform sit in one.
 template <int PADSHIFT>
 struct SmemLaneFast {
   static constexpr bool kLaneFast = true;
@@ -360,6 +377,7 @@ struct SmemLaneFast {
   static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
   BBT_HD cf& ref(int s) const { return base[s * G + g]; }
   BBT_HD cf& at(int p) const { return ref(slot(p)); }
+  static BBT_HD void sync() { BBT_SYNC(); }
 };
 template <int PADSHIFT>
 struct SmemLaneSlow {
@@ -368,18 +386,20 @@ struct SmemLaneSlow {
   static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
   BBT_HD cf& ref(int s) const { return base[s]; }
   BBT_HD cf& at(int p) const { return ref(slot(p)); }
+  static BBT_HD void sync() { BBT_SYNC(); }
 };
-
-#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-#define BBT_SYNC() __syncthreads()
-#elif defined(BBT_EMULATE)
-}  // namespace bbt
-void bbt_emu_syncthreads();
-namespace bbt {
-#define BBT_SYNC() bbt_emu_syncthreads()
-#else
-#define BBT_SYNC()
-#endif
+// A transform whose threads all belong to one warp (at most 32 x E points):
+// exchanges need only a warp-level barrier, so the warps of a CTA run their
+// transforms independently of one another.
+template <int PADSHIFT>
+struct SmemWarp {
+  static constexpr bool kLaneFast = false;
+  cf* base;  // this transform's private region
+  static BBT_HD int slot(int p) { return p + (p >> PADSHIFT); }
+  BBT_HD cf& ref(int s) const { return base[s]; }
+  BBT_HD cf& at(int p) const { return ref(slot(p)); }
+  static BBT_HD void sync() { BBT_SYNCWARP(); }
+};
 
 // Streaming access to data that is touched once: do not let it displace the
 // twiddle tables in L1.
@@ -537,7 +557,7 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
   }
   if constexpr ((1 << (LOG2NS + LOG2R)) != C::N) {
     constexpr int PADN = 1 << C::PADSHIFT;
-    BBT_SYNC();
+    Smem::sync();
     if constexpr (C::T % PADN == 0) {
       const int s0 = Smem::slot(t);
 #pragma unroll
@@ -547,7 +567,7 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
 #pragma unroll
       for (int e = 0; e < C::E; ++e) v[e] = sm.at(t + C::T * e);
     }
-    BBT_SYNC();
+    Smem::sync();
   }
 }
 
@@ -567,6 +587,35 @@ struct FftStages {
 template <class C, class Smem>
 BBT_HD void block_fft(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
   if constexpr (C::Plan::NS > 0) FftStages<C, 0, Smem>::run(v, t, tw, sm);
+}
+
+// The same transform in two parts: `head` runs every stage that ends with an
+// exchange through shared memory, `tail` the last one, which works in
+// registers only.  Between the two the exchange buffer is free (every thread
+// has passed the barrier after its last read), so a kernel can let an
+// asynchronous copy of its next tile land there while the tail runs.
+template <class C, int STAGE, int END, class Smem>
+struct FftStageRange {
+  static BBT_HD void run(cf* v, int t, const cf* __restrict__ tw,
+                         const Smem& sm) {
+    if constexpr (STAGE < END) {
+      using P = typename C::Plan;
+      fft_stage<C, P::before(STAGE), P::bits(STAGE), Smem>(v, t, tw, sm);
+      FftStageRange<C, STAGE + 1, END, Smem>::run(v, t, tw, sm);
+    }
+  }
+};
+template <class C, class Smem>
+BBT_HD void block_fft_head(cf* v, int t, const cf* __restrict__ tw,
+                           const Smem& sm) {
+  if constexpr (C::Plan::NS > 1)
+    FftStageRange<C, 0, C::Plan::NS - 1, Smem>::run(v, t, tw, sm);
+}
+template <class C, class Smem>
+BBT_HD void block_fft_tail(cf* v, int t, const cf* __restrict__ tw,
+                           const Smem& sm) {
+  if constexpr (C::Plan::NS > 0)
+    FftStageRange<C, C::Plan::NS - 1, C::Plan::NS, Smem>::run(v, t, tw, sm);
 }
 
 }  // namespace bbt

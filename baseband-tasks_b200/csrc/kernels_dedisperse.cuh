@@ -21,6 +21,7 @@
 // For N <= 16384 a single kernel (dd_small) does everything in one round trip.
 #pragma once
 #include "kernels_fft.cuh"
+#include "tma.cuh"
 
 namespace bbt {
 
@@ -30,6 +31,7 @@ struct DdArgs {
   cf* work;             // n_frames * N * S scratch
   const cf* tw;         // N2-th roots of unity (row FFTs, single-pass frames)
   const cf* tw1;        // N1-th roots of unity (column FFTs)
+  const cf* tw_sub;     // (N2/32)-th roots of unity (dd_row2_kernel)
   BigTwiddle big;       // W_N^m
   const cf* chirp;      // [n_chirp][N1][N2]
   const int* series_map;  // series -> chirp index
@@ -346,6 +348,449 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   }
 }
 
+// Pass 2 for the planar layout as a persistent kernel fed by bulk copies (TMA):
+// one CTA per SM walks over the tiles (G consecutive rows = one contiguous
+// 128 KB range).  The exchange buffer is idle from the last exchange of the
+// inverse transform until the first one of the next tile; in that window one
+// thread lets a bulk copy (cp.async.bulk, completion on an mbarrier) bring the
+// next tile into it, out of L2, where a bulk prefetch issued a tile earlier
+// has put it.  The per-thread global loads, their address arithmetic and the
+// per-line L2 prefetches of dd_row_kernel are gone: a tile starts with
+// conflict-free reads from shared memory.
+#if defined(__CUDACC__)
+#define BBT_DEV_NOINLINE __device__ __noinline__
+#else
+#define BBT_DEV_NOINLINE static __attribute__((noinline))
+#endif
+// One tile of the persistent row pass.  Kept out of line so that the compiler
+// treats it like the body of a one-tile kernel: inlined into the tile loop,
+// loop-invariant address arithmetic was hoisted into registers the butterflies
+// need (300 bytes of spills at the 128-register cap).
+template <class C>
+BBT_DEV_NOINLINE void dd_row_tma_tile(
+    cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw, bool valid,
+    unsigned phase, const char* next_src, unsigned next_bytes) {
+  const int tid = threadIdx.x;
+  const int t = tid % C::T, g = tid / C::T;
+  constexpr unsigned kChunk = 32 * 1024;            // bytes per bulk copy
+  mbar_wait(bar, phase & 1u, phase);
+  cf v[C::E];
+  {
+    const cf* land = smem + g * C::N + t;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      v[e] = valid ? land[C::T * e] : mk(0.f, 0.f);
+  }
+  BBT_SYNC();  // the landing zone becomes the exchange buffer
+  SmemLaneSlow<C::PADSHIFT> sm{smem + (size_t)g * C::NPAD};
+  block_fft<C>(v, t, tw, sm);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      v[e] = cconj(cmul(v[e], ldtw(chirp, t + C::T * e)));
+  }
+  block_fft_head<C>(v, t, tw, sm);
+  // Every thread is past its last read of the exchange buffer: the next
+  // tile may land there while the last butterflies and the stores run.
+  if (tid == 0 && next_bytes) {
+    fence_proxy_async();  // the exchanges wrote here through the generic proxy
+    mbar_expect_tx(bar, next_bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < next_bytes; o += kChunk)
+      bulk_load(dst + o, next_src + o,
+                next_bytes - o < kChunk ? next_bytes - o : kChunk, bar,
+                o + kChunk >= next_bytes);
+  }
+  block_fft_tail<C>(v, t, tw, sm);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) row[t + C::T * e] = v[e];
+  }
+}
+
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
+  cf* smem = BBT_SMEM(cf);
+  Mbar* bar = reinterpret_cast<Mbar*>(smem + C::SMEM_BYTES / sizeof(cf));
+  const unsigned n1 = (unsigned)(a.N >> a.log2n2);
+  const unsigned S = (unsigned)a.S;
+  const unsigned rows = n1 * S;                     // rows per frame
+  const unsigned tiles_per_frame = (rows + C::G - 1) / C::G;
+  const unsigned n_tiles = tiles_per_frame * (unsigned)a.n_frames;
+  const int tid = threadIdx.x;
+  const int t = tid % C::T, g = tid / C::T;
+  constexpr unsigned kChunk = 32 * 1024;            // bytes per bulk copy
+  // Tile `lin`: frames vary fastest, so CTAs that run together share chirp rows.
+  auto tile_base = [&](unsigned lin, unsigned& rho0) -> cf* {
+    const unsigned xblk = lin / (unsigned)a.n_frames;
+    const unsigned frame = lin - xblk * (unsigned)a.n_frames;
+    rho0 = xblk * C::G;
+    return a.work + (long long)frame * a.N * a.S + (long long)rho0 * C::N;
+  };
+  auto tile_bytes = [&](unsigned rho0) -> unsigned {
+    const unsigned left = rows - rho0;
+    return (left < (unsigned)C::G ? left : (unsigned)C::G) * C::N *
+           (unsigned)sizeof(cf);
+  };
+  if (tid == 0) mbar_init(bar, 1);
+  BBT_SYNC();
+  if (tid == 0 && blockIdx.x < n_tiles) {
+    unsigned rho0;
+    const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
+    const unsigned bytes = tile_bytes(rho0);
+    mbar_expect_tx(bar, bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < bytes; o += kChunk)
+      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
+                o + kChunk >= bytes);
+  }
+  unsigned k = 0;
+#pragma unroll 1
+  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+    unsigned rho0;
+    cf* row = tile_base(lin, rho0) + (long long)g * C::N;
+    const unsigned rho = rho0 + g;
+    const bool valid = rho < rows;
+    const unsigned k1 = rho / S, s = rho - k1 * S;
+    const cf* chirp = a.chirp;
+    if (valid) chirp += ((long long)a.series_map[s] * n1 + k1) * C::N;
+    // Into L2 meanwhile: this tile's chirp rows and the next tile.
+    if (valid && t == 0)
+      for (unsigned o = 0; o < C::N * sizeof(cf); o += kChunk)
+        bulk_prefetch_l2(reinterpret_cast<const char*>(chirp) + o,
+                         C::N * sizeof(cf) - o < kChunk
+                             ? (unsigned)(C::N * sizeof(cf)) - o : kChunk);
+    const unsigned next = lin + gridDim.x;
+    const char* next_src = nullptr;
+    unsigned next_bytes = 0;
+    if (next < n_tiles) {
+      unsigned r0;
+      next_src = reinterpret_cast<const char*>(tile_base(next, r0));
+      next_bytes = tile_bytes(r0);
+      if (tid == 32)
+        for (unsigned o = 0; o < next_bytes; o += kChunk)
+          bulk_prefetch_l2(next_src + o,
+                           next_bytes - o < kChunk ? next_bytes - o : kChunk);
+    }
+    dd_row_tma_tile<C>(smem, bar, row, chirp, a.tw, valid, k, next_src,
+                       next_bytes);
+  }
+}
+
+// Pass 2, second formulation: the N2-point transforms are split as 32 x M
+// (M = N2/32) so that only ONE exchange per transform needs the whole CTA.
+//   forward:  radix-32 butterflies over e of x[u + M e] in the thread that
+//             loaded them, x W_N2^{u k1}, transpose through shared memory,
+//             then 32 independent M-point transforms over u, each done by
+//             M/32 threads of ONE warp (exchange with __syncwarp only);
+//             bin k1 + 32 k2 ends up in the sub-transform k1, position k2.
+//   multiply by the chirp (stored in that order, see row2_pos), conjugate;
+//   mirror:   the M-point transforms over k2, x W_N2^{k1 u}, transpose back,
+//             radix-32 butterflies over k1 in the thread that stores
+//             out[u + M e] -- natural order, coalesced.
+// Between the two transposes every warp runs two M-point transforms, the
+// chirp multiply and the twiddles without waiting for any other warp, so the
+// butterflies of some warps overlap the exchanges and chirp loads of others
+// (in dd_row_kernel every exchange is a CTA-wide barrier pair and the FP32
+// pipe idles while shared memory is busy, and vice versa).  Data movement is
+// that of dd_row_tma_kernel: persistent CTAs, bulk copies into the exchange
+// buffer, results stored from registers.
+//
+// Position within a stored chirp row of the bin kk = q1 + 32 (tt + Ts e) of
+// that row (Ts = M/32 threads per sub-transform): the thread with index
+// q1 Ts + tt in its row reads its e-th value at e M + q1 Ts + tt.
+BBT_HD long long row2_pos(long long kk, int log2n2) {
+  const long long M = 1LL << (log2n2 - 5), Ts = M >> 5 ? M >> 5 : 1;
+  const long long q1 = kk & 31, q2 = kk >> 5;
+  if (M < 32) return kk;  // not used below 1024 points
+  return (q2 / Ts) * M + q1 * Ts + (q2 % Ts);
+}
+BBT_HD long long row2_bin(long long pos, int log2n2) {  // inverse of row2_pos
+  const long long M = 1LL << (log2n2 - 5), Ts = M >> 5 ? M >> 5 : 1;
+  if (M < 32) return pos;
+  const long long e = pos / M, rem = pos % M;
+  return (rem / Ts) + 32 * ((rem % Ts) + Ts * e);
+}
+
+template <class C>
+struct Row2Cfg {
+  static constexpr int M = C::T;                    // points per sub-transform
+  static constexpr int Ts = M / 32;                 // its threads
+  using CS = FftCfg<C::LOG2N - 5, 5, Ts>;           // the M-point transform
+  static constexpr int P = CS::NPAD > M ? CS::NPAD : M;  // pitch of a row of X
+  static constexpr size_t kElems =
+      (size_t)C::G * 32 * P > C::SMEM_BYTES / sizeof(cf)
+          ? (size_t)C::G * 32 * P : C::SMEM_BYTES / sizeof(cf);
+  static constexpr size_t kSmemBytes = kElems * sizeof(cf) + sizeof(Mbar);
+};
+
+template <class C>
+BBT_DEV_NOINLINE void dd_row2_tile(
+    cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw,
+    const cf* tw_sub, bool valid, unsigned phase, const char* next_src,
+    unsigned next_bytes) {
+  static_assert(C::LOG2E == 5 && C::LOG2N >= 10, "32 values per thread");
+  using R = Row2Cfg<C>;
+  using CS = typename R::CS;
+  constexpr int M = R::M, Ts = R::Ts, P = R::P;
+  static_assert(CS::T == Ts && CS::G == 1 && CS::N == M && 32 % Ts == 0,
+                "a sub-transform sits in one warp");
+  const int tid = threadIdx.x;
+  const int u = tid % C::T, g = tid / C::T;
+  const int k1 = u / Ts, tt = u % Ts;        // sub-transform and place in it
+  constexpr unsigned kChunk = 32 * 1024;
+  cf* X = smem + (size_t)g * 32 * P;         // this row's [32][P] matrix
+  mbar_wait(bar, phase & 1u, phase);
+  cf v[32];
+  {
+    const cf* land = smem + g * C::N + u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = valid ? land[M * e] : mk(0.f, 0.f);
+  }
+  BBT_SYNC();  // the landing zone becomes the exchange buffer
+  // Forward: over e in this thread, twiddle, transpose.
+  Dft<32>::run(v);
+  apply_twiddles<32>(v, tw, u);
+#pragma unroll
+  for (int r = 0; r < 32; ++r) X[r * P + u] = v[r];
+  BBT_SYNC();
+  // From here to the next barrier warps do not wait for one another.
+  cf* mine = X + k1 * P;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = mine[tt + Ts * e];
+  BBT_SYNCWARP();
+  SmemWarp<CS::PADSHIFT> sw{mine};
+  block_fft<CS>(v, tt, tw_sub, sw);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      v[e] = cconj(cmul(v[e], ldtw(chirp, u + M * e)));
+  }
+  block_fft<CS>(v, tt, tw_sub, sw);
+  {
+    // x W_N2^{k1 (tt + Ts e)}: a ramp in e from a few table look-ups.
+    cf pw[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) pw[b] = ldtw(tw, (k1 * Ts) << b);
+    Ramp<5, 0>::run(v, ldtw(tw, k1 * tt), pw);
+  }
+  BBT_SYNCWARP();  // the sub-transform's last reads of this row of X
+#pragma unroll
+  for (int e = 0; e < 32; ++e) mine[tt + Ts * e] = v[e];
+  BBT_SYNC();
+#pragma unroll
+  for (int r = 0; r < 32; ++r) v[r] = X[r * P + u];
+  BBT_SYNC();  // X is free: the next tile may land while we finish
+  if (tid == 0 && next_bytes) {
+    fence_proxy_async();
+    mbar_expect_tx(bar, next_bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < next_bytes; o += kChunk)
+      bulk_load(dst + o, next_src + o,
+                next_bytes - o < kChunk ? next_bytes - o : kChunk, bar,
+                o + kChunk >= next_bytes);
+  }
+  Dft<32>::run(v);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) row[u + M * e] = v[e];
+  }
+}
+
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
+  cf* smem = BBT_SMEM(cf);
+  Mbar* bar = reinterpret_cast<Mbar*>(smem + Row2Cfg<C>::kElems);
+  const unsigned n1 = (unsigned)(a.N >> a.log2n2);
+  const unsigned S = (unsigned)a.S;
+  const unsigned rows = n1 * S;
+  const unsigned tiles_per_frame = (rows + C::G - 1) / C::G;
+  const unsigned n_tiles = tiles_per_frame * (unsigned)a.n_frames;
+  const int tid = threadIdx.x;
+  const int t = tid % C::T, g = tid / C::T;
+  constexpr unsigned kChunk = 32 * 1024;
+  auto tile_base = [&](unsigned lin, unsigned& rho0) -> cf* {
+    const unsigned xblk = lin / (unsigned)a.n_frames;
+    const unsigned frame = lin - xblk * (unsigned)a.n_frames;
+    rho0 = xblk * C::G;
+    return a.work + (long long)frame * a.N * a.S + (long long)rho0 * C::N;
+  };
+  auto tile_bytes = [&](unsigned rho0) -> unsigned {
+    const unsigned left = rows - rho0;
+    return (left < (unsigned)C::G ? left : (unsigned)C::G) * C::N *
+           (unsigned)sizeof(cf);
+  };
+  if (tid == 0) mbar_init(bar, 1);
+  BBT_SYNC();
+  if (tid == 0 && blockIdx.x < n_tiles) {
+    unsigned rho0;
+    const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
+    const unsigned bytes = tile_bytes(rho0);
+    mbar_expect_tx(bar, bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < bytes; o += kChunk)
+      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
+                o + kChunk >= bytes);
+  }
+  unsigned k = 0;
+#pragma unroll 1
+  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+    unsigned rho0;
+    cf* row = tile_base(lin, rho0) + (long long)g * C::N;
+    const unsigned rho = rho0 + g;
+    const bool valid = rho < rows;
+    const unsigned k1 = rho / S, s = rho - k1 * S;
+    const cf* chirp = a.chirp;
+    if (valid) chirp += ((long long)a.series_map[s] * n1 + k1) * C::N;
+    if (valid && t == 0)
+      for (unsigned o = 0; o < C::N * sizeof(cf); o += kChunk)
+        bulk_prefetch_l2(reinterpret_cast<const char*>(chirp) + o,
+                         C::N * sizeof(cf) - o < kChunk
+                             ? (unsigned)(C::N * sizeof(cf)) - o : kChunk);
+    const unsigned next = lin + gridDim.x;
+    const char* next_src = nullptr;
+    unsigned next_bytes = 0;
+    if (next < n_tiles) {
+      unsigned r0;
+      next_src = reinterpret_cast<const char*>(tile_base(next, r0));
+      next_bytes = tile_bytes(r0);
+      if (tid == 32)
+        for (unsigned o = 0; o < next_bytes; o += kChunk)
+          bulk_prefetch_l2(next_src + o,
+                           next_bytes - o < kChunk ? next_bytes - o : kChunk);
+    }
+    dd_row2_tile<C>(smem, bar, row, chirp, a.tw, a.tw_sub, valid, k, next_src,
+                    next_bytes);
+  }
+}
+
+// Passes 1 and 3 as persistent kernels fed by tensor-map bulk copies (TMA).
+// A column tile is N1 rows of G lanes (128 bytes), rows N2*S*8 bytes apart: one
+// cp.async.bulk.tensor box of [<=256 rows][G lanes] per quarter of the tile,
+// which lands in shared memory already in the lane-fastest layout the block
+// FFT exchanges in.  As in dd_row_tma_kernel the exchange buffer doubles as
+// the landing zone: the copy of the next tile is issued right after the last
+// exchange, and overlaps the last butterfly stage, the twiddle ramp and the
+// stores.  For the planar work buffer (pass 3) the box is [rows][S][G/S]: the
+// de-interleaving gather is done by the copy engine, lane g of the tile being
+// series g / (G/S), column n2_0 + g % (G/S).
+struct DdColTma {
+  int n_boxes;      // copies per tile
+  int box_rows;     // rows per copy
+  int tn;           // planar source: n2 values per series in a tile (G / S)
+};
+
+template <class C, bool INVERSE>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    dd_col_tma_kernel(DdArgs a, DdColTma m, BBT_TMAP_PARAM map) {
+  cf* smem = BBT_SMEM(cf);
+  // The barrier sits behind the exchange buffer (or the landing zone, for
+  // transforms without an exchange).
+  constexpr size_t kTile = (size_t)C::N * C::G;          // elements
+  constexpr size_t kBuf = C::SMEM_BYTES / sizeof(cf) > kTile
+                              ? C::SMEM_BYTES / sizeof(cf) : kTile;
+  Mbar* bar = reinterpret_cast<Mbar*>(smem + kBuf);
+  const unsigned N2 = (unsigned)(a.N >> a.log2n1);
+  const unsigned S = (unsigned)a.S;
+  const unsigned n2s = N2 * S;
+  const unsigned nblk = (n2s + C::G - 1) / C::G;
+  const unsigned n_tiles = nblk * (unsigned)a.n_frames;
+  const int tid = threadIdx.x;
+  const int g = tid % C::G, t = tid / C::G;
+  const bool planar_src = INVERSE && a.planar;
+  auto issue = [&](unsigned lin) {                  // one thread
+    const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
+    fence_proxy_async();
+    mbar_expect_tx(bar, (unsigned)(kTile * sizeof(cf)));
+    for (int q = 0; q < m.n_boxes; ++q) {
+      cf* dst = smem + (size_t)q * m.box_rows * C::G;
+      const bool last = q == m.n_boxes - 1;
+      if (planar_src)
+        tensor_load_3d(dst, &map, (int)(c0 / S), 0,
+                       (int)(frame * C::N + q * m.box_rows), bar, last);
+      else
+        tensor_load_3d(dst, &map, (int)c0, q * m.box_rows, (int)frame, bar,
+                       last);
+    }
+  };
+  auto prefetch = [&](unsigned lin) {
+    const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
+    for (int q = 0; q < m.n_boxes; ++q) {
+      if (planar_src)
+        tensor_prefetch_3d(&map, (int)(c0 / S), 0,
+                           (int)(frame * C::N + q * m.box_rows));
+      else
+        tensor_prefetch_3d(&map, (int)c0, q * m.box_rows, (int)frame);
+    }
+  };
+  if (tid == 0) mbar_init(bar, 1);
+  BBT_SYNC();
+  if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x);
+  unsigned k = 0;
+#pragma unroll 1
+  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+    const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
+    // Flat column n2*S + s of this lane.
+    unsigned n2, sser;
+    if (planar_src) {
+      sser = (unsigned)g / (unsigned)m.tn;
+      n2 = c0 / S + ((unsigned)g - sser * (unsigned)m.tn);
+    } else {
+      const unsigned col = c0 + g;
+      n2 = col / S;
+      sser = col - n2 * S;
+    }
+    const bool valid = n2 < N2 && sser < S;
+    const unsigned next = lin + gridDim.x;
+    if (tid == 32 && next < n_tiles) prefetch(next);
+    mbar_wait(bar, k & 1u, k);
+    cf v[C::E];
+    {
+      const cf* land = smem + (size_t)t * C::G + g;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) v[e] = land[(size_t)e * C::T * C::G];
+    }
+    BBT_SYNC();  // the landing zone becomes the exchange buffer
+    if (INVERSE && valid) col_twiddle<C, 0>(v, a.big, (int)n2, t, a.scale);
+    SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+    block_fft_head<C>(v, t, a.tw1, sm);
+    if (tid == 0 && next < n_tiles) issue(next);
+    block_fft_tail<C>(v, t, a.tw1, sm);
+    if (!valid) continue;
+    if (!INVERSE) {
+      col_twiddle<C, 0>(v, a.big, (int)n2, t, 1.f);
+      cf* dst = a.work + (long long)frame * a.N * a.S;
+      long long step;
+      if (a.planar) {
+        dst += (long long)sser * N2 + n2;
+        step = (long long)a.S * N2;
+      } else {
+        dst += (long long)n2 * S + sser;
+        step = n2s;
+      }
+      dst += (long long)t * step;
+      const long long pstep = (long long)C::T * step;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        *dst = v[e];
+        dst += pstep;
+      }
+    } else {
+      const long long col = (long long)n2 * S + sser;
+      long long flat = (long long)t * n2s + col;
+      const long long fstep = (long long)C::T * n2s;
+      cf* dst = a.out + (long long)frame * a.out_frame_stride - a.out_shift +
+                flat;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        if (flat >= a.lo && flat < a.hi) *dst = cconj(v[e]);
+        flat += fstep;
+        dst += fstep;
+      }
+    }
+  }
+}
+
 // Single pass for N <= 16384: lanes are (frame, series) pairs, series fastest.
 // LANEFAST (S > 1): consecutive threads take consecutive series; otherwise
 // consecutive threads walk along time.
@@ -392,6 +837,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
 //   chirp = exp(2 pi i phase)
 // stored at [c][k1][k2] for bin k = k1 + N1*k2.
 struct ChirpArgs {
+  int row2_log2n2;          // > 0: rows stored in dd_row2_kernel's order
   cf* chirp;
   const double* freq_mhz;   // [n_chirp]
   const double* fref_mhz;   // [n_chirp]
@@ -408,7 +854,9 @@ BBT_GLOBAL void chirp_kernel(ChirpArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long c = i / a.N, r = i % a.N;
-    const long long k1 = r / n2, k2 = r % n2;
+    const long long k1 = r / n2;
+    long long k2 = r % n2;
+    if (a.row2_log2n2 > 0) k2 = row2_bin(k2, a.row2_log2n2);
     const long long k = k1 + a.n1 * k2;
     const long long ks = (k < (a.N + 1) / 2) ? k : k - a.N;  // np.fft.fftfreq
     const double fftfreq = (double)ks * (a.rate_mhz / (double)a.N);
@@ -427,13 +875,16 @@ BBT_GLOBAL void chirp_kernel(ChirpArgs a) {
 // Scatter a caller-supplied response (natural bin order, [n_chirp][N]) into
 // the [c][k1][k2] layout; lets Convolve-style tasks reuse the plan.
 BBT_GLOBAL void chirp_scatter_kernel(cf* dst, const cf* src, long long N,
-                                     long long n1, long long n_chirp) {
+                                     long long n1, long long n_chirp,
+                                     int row2_log2n2) {
   const long long n2 = N / n1;
   const long long total = n_chirp * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long c = i / N, r = i % N;
-    dst[i] = src[c * N + (r / n2) + n1 * (r % n2)];
+    long long k2 = r % n2;
+    if (row2_log2n2 > 0) k2 = row2_bin(k2, row2_log2n2);
+    dst[i] = src[c * N + (r / n2) + n1 * k2];
   }
 }
 

@@ -6,6 +6,7 @@
 //   fold                integration.py:380-395 (phase-bin scatter add)
 #pragma once
 #include "kernels_fft.cuh"
+#include "tma.cuh"
 
 namespace bbt {
 
@@ -224,6 +225,132 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
     if (tid == 0 && blockIdx.x == 0 && hi > lo)
       atomic_add(a.count + b, (unsigned long long)(hi - lo));
   }
+}
+
+// The same for narrow samples (M = 1, 2 or 4 polarization pairs per time
+// sample), fed by bulk asynchronous copies: the G/2 units of a CTA are then
+// G/2/M adjacent spectra of all M series, i.e. one contiguous 64 KB block of
+// the input per tile, which one thread copies into a two-deep ring in shared
+// memory (cp.async.bulk, completion counted on an mbarrier) while the other
+// tile is transformed.  No per-thread loads, address arithmetic or L2
+// prefetches are left; DRAM latency is covered by the two tiles in flight.
+// Stage layout: [jl][i][m][p] with 64 bytes of padding between the spectra
+// jl so that the 8 lanes x 4 time samples a warp reads fall in distinct banks.
+template <class C>
+struct ChanPowTma {
+  static constexpr int kStages = 2;
+  static BBT_HD constexpr long long spectrum_elems(long long M) {
+    return (long long)C::N * M * 2;
+  }
+  static BBT_HD constexpr long long stage_elems(long long M) {
+    return (C::G / 2 / M) * (spectrum_elems(M) + 8);
+  }
+  static BBT_HD constexpr size_t smem_bytes(long long M) {
+    return C::SMEM_BYTES + kStages * stage_elems(M) * sizeof(cf) +
+           kStages * sizeof(Mbar);
+  }
+};
+
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
+    chanpow_tma_kernel(ChanPowArgs a) {
+  static_assert(C::G % 2 == 0 && C::E % 2 == 0, "pairs of lanes and values");
+  using K = ChanPowTma<C>;
+  cf* smem = BBT_SMEM(cf);
+  const int tid = threadIdx.x;
+  const int g = tid % C::G, t = tid / C::G;
+  const int p = g & 1;
+  const int M = (int)a.M;
+  const int nj = C::G / 2 / M;                 // spectra per tile
+  const long long jsub0 = (long long)blockIdx.x * nj;
+  const int jl = (g >> 1) / M;                 // this lane's spectrum in tile
+  const long long m = (g >> 1) - jl * M, jsub = jsub0 + jl;
+  const long long b = a.b_first + blockIdx.y;
+  long long lo = a.offsets[b] - a.j_first, hi = a.offsets[b + 1] - a.j_first;
+  if (lo < 0) lo = 0;
+  if (hi > a.n_spec) hi = a.n_spec;
+  const bool lane_ok = jsub < a.msub;
+  const long long spec = K::spectrum_elems(M);   // complex values per spectrum
+  cf* ring = smem + C::SMEM_BYTES / sizeof(cf);
+  Mbar* bars = reinterpret_cast<Mbar*>(ring + K::kStages * K::stage_elems(M));
+  const cf* in = reinterpret_cast<const cf*>(a.in);
+  f4 acc[C::E / 2];
+#pragma unroll
+  for (int i = 0; i < C::E / 2; ++i)
+    acc[i].x = acc[i].y = acc[i].z = acc[i].w = 0.f;
+  if (tid == 0)
+    for (int s = 0; s < K::kStages; ++s) mbar_init(bars + s, 1);
+  BBT_SYNC();
+  const long long n_iter = hi > lo ? (hi - lo + a.msub - 1) / a.msub : 0;
+  // Spectra of this CTA's tile that exist in iteration `it`.
+  auto n_valid = [&](long long it) -> int {
+    const long long j0 = lo + it * a.msub;
+    long long end = j0 + a.msub;
+    if (end > hi) end = hi;
+    long long n = end - (j0 + jsub0);
+    return n < 0 ? 0 : (n > nj ? nj : (int)n);
+  };
+  auto issue = [&](long long it, int s) {        // one thread
+    const int nv = n_valid(it);
+    Mbar* bar = bars + s;
+    if (nv == 0) {
+      mbar_arrive(bar);
+      return;
+    }
+    const cf* src = in + (lo + it * a.msub + jsub0) * spec;
+    cf* dst = ring + s * K::stage_elems(M);
+    mbar_expect_tx(bar, (uint32_t)(nv * spec * sizeof(cf)));
+    for (int q = 0; q < nv; ++q)
+      bulk_load(dst + q * (spec + 8), src + q * spec,
+                (uint32_t)(spec * sizeof(cf)), bar, q == nv - 1);
+  };
+  if (tid == 0)
+    for (int s = 0; s < K::kStages; ++s)
+      if (s < n_iter) issue(s, s);
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  const cf* mine = ring + jl * (spec + 8) + (long long)t * (2 * M) + (m * 2 + p);
+  for (long long it = 0; it < n_iter; ++it) {
+    const int s = (int)(it % K::kStages);
+    const bool valid = lane_ok && jl < n_valid(it);
+    mbar_wait(bars + s, (uint32_t)(it / K::kStages) & 1u,
+              (uint32_t)(it / K::kStages));
+    cf v[C::E];
+    const cf* src = mine + s * K::stage_elems(M);
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      v[e] = valid ? src[(long long)e * C::T * (2 * M)] : mk(0.f, 0.f);
+    BBT_SYNC();  // every thread has taken its values: the stage is free
+    if (tid == 0 && it + K::kStages < n_iter) issue(it + K::kStages, s);
+    block_fft<C>(v, t, a.tw, sm);
+#pragma unroll
+    for (int i = 0; i < C::E / 2; ++i) {
+      const cf keep = p ? v[2 * i + 1] : v[2 * i];
+      const cf send = p ? v[2 * i] : v[2 * i + 1];
+      cf other;
+      other.x = shfl_xor1(send.x);
+      other.y = shfl_xor1(send.y);
+      const f4 q = p ? stokes_like(other, keep) : stokes_like(keep, other);
+      acc[i].x += q.x;
+      acc[i].y += q.y;
+      acc[i].z += q.z;
+      acc[i].w += q.w;
+    }
+  }
+  if (lane_ok && hi > lo) {
+    const float w =
+        a.average ? (float)(a.offsets[b + 1] - a.offsets[b]) : 1.f;
+#pragma unroll
+    for (int i = 0; i < C::E / 2; ++i) {
+      const int k = t + C::T * (2 * i + p);
+      float* o = a.out + ((b * C::N + k) * a.M + m) * 4;
+      atomic_add(o + 0, acc[i].x / w);
+      atomic_add(o + 1, acc[i].y / w);
+      atomic_add(o + 2, acc[i].z / w);
+      atomic_add(o + 3, acc[i].w / w);
+    }
+  }
+  if (tid == 0 && blockIdx.x == 0 && hi > lo)
+    atomic_add(a.count + b, (unsigned long long)(hi - lo));
 }
 
 // ---------------------------------------------------------------------------

@@ -34,6 +34,8 @@ struct alignas(8) Mbar {
 inline void mbar_init(Mbar* b, int) { b->phases_done.store(0); }
 inline void mbar_expect_tx(Mbar*, uint32_t) {}
 inline void mbar_complete_emu(Mbar* b) { b->phases_done.fetch_add(1); }
+// Complete a phase without any bytes (an empty tile).
+inline void mbar_arrive(Mbar* b) { mbar_complete_emu(b); }
 // Wait until phase number `k` (0-based count of completed phases) is done.
 inline void mbar_wait(Mbar* b, uint32_t parity, uint32_t k_phase) {
   (void)parity;
@@ -121,6 +123,11 @@ __device__ __forceinline__ void mbar_expect_tx(Mbar* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
                    smem_u32(b)),
                "r"(bytes)
+               : "memory");
+}
+// Complete a phase without any bytes (an empty tile).
+__device__ __forceinline__ void mbar_arrive(Mbar* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b))
                : "memory");
 }
 // k_phase is only used by the emulation.

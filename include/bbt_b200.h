@@ -198,6 +198,10 @@ int bbt_average_exec(const void* sum, const void* count, void* out,
  * bbt_profile_report: wait for them and write "kernel count total_ms" lines
  * (NUL-terminated) into buf, clearing the records. */
 int64_t bbt_launch_count(void);
+/* Force a kernel variant for A/B measurements (see DESIGN.md section 4 for
+ * the keys); the environment variable BBT_TUNE="key=value,..." does the same
+ * at start-up.  Results do not depend on the variant. */
+int bbt_tune_set(const char* key, int value);
 int bbt_profile_enable(int on);
 int bbt_profile_report(char* buf, int64_t size);
 

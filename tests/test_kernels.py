@@ -247,7 +247,10 @@ INTER, PLANAR, HALF, FULLROW = 512, 256, 4096 | 8192, 16384   # plan hints
     (13, 16, INTER), (15, 3, 5 | INTER | FULLROW), (15, 5, 5 | PLANAR),
     (15, 2, 5 | HALF), (14, 16, 4 | INTER | HALF), (14, 7, 3 | INTER),
     (20, 2, 0), (20, 16, 0), (20, 16, INTER | FULLROW), (20, 16, 6 | PLANAR),
-    (22, 2, 10), (24, 2, 0), (21, 3, 0)])
+    (22, 2, 10), (24, 2, 0), (21, 3, 0),
+    # planar rows of 2^11 .. 2^14 points (warp-local sub-transforms)
+    (13, 2, 2 | PLANAR), (14, 1, 2 | PLANAR), (15, 1, 2 | PLANAR),
+    (15, 1, 1 | PLANAR), (16, 3, 2 | PLANAR)])
 def test_dedisperse_large(backend, log2n, S, log2n1):
     if log2n > 16 and not backend.big:
         pytest.skip('too slow on host threads')
@@ -344,7 +347,12 @@ def test_channelize_power(backend, n, m, n_spec):
 
 @pytest.mark.parametrize('n,m,n_spec,ratio', [(16, 2, 200, 7.8125),
                                               (64, 1, 50, 2.26),
-                                              (1024, 8, 17, 4.)])
+                                              (1024, 8, 17, 4.),
+                                              # narrow samples: bulk-copy path
+                                              (1024, 1, 23, 5.5),
+                                              (1024, 2, 19, 4.),
+                                              (1024, 4, 9, 3.),
+                                              (512, 1, 40, 13.)])
 def test_channelize_power_integrate(backend, n, m, n_spec, ratio):
     rng = np.random.default_rng(n + m + 1)
     x = cnoise(rng, (n_spec * n, m, 2))
