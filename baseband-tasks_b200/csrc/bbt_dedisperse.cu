@@ -50,6 +50,7 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
   m.box_rows = C::N < 256 ? C::N : 256;
   m.n_boxes = C::N / m.box_rows;
   m.tn = 1;
+  m.stagger_ns = C::THREADS <= 256 ? tune("col_stagger_ns", 0) : 0;
   TensorMap map;
   uint64_t dims[3], strides[3];
   uint32_t box[3];
@@ -75,8 +76,12 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
   if (make_tensor_map(&map, base, 8, 3, dims, strides, box))
     return BBT_EUNSUPPORTED;
   constexpr size_t kTile = (size_t)C::N * C::G * sizeof(cf);
-  const size_t smem =
-      (C::SMEM_BYTES > kTile ? C::SMEM_BYTES : kTile) + sizeof(Mbar);
+  // Behind the tile: the barrier and the twiddle tables of the kernel.
+  constexpr int LE = C::LOG2E > 0 ? C::LOG2E : 1;
+  const size_t smem = (C::SMEM_BYTES > kTile ? C::SMEM_BYTES : kTile) +
+                      2 * sizeof(Mbar) +
+                      (LE * C::G + 2 * C::T + 16) * sizeof(cf);
+  m.fast_tw = (C::G % S == 0 || planar_src) && tune("col_fast_tw", 1);
   const int64_t tiles = ceil_div(n2s, C::G) * n_frames;
   const int per_sm = C::THREADS <= 256 ? 2 : 1;
   const int64_t ctas = std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
@@ -243,6 +248,7 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->big_lo = p->big_hi = p->chirp = nullptr;
   p->series_map = nullptr;
   p->planar = 1;
+  if (!hint) hint = tune("dd_hint", 0);
   p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
   const int hint_l1 = hint & 0xff;
   const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;

@@ -674,10 +674,21 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
 // stores.  For the planar work buffer (pass 3) the box is [rows][S][G/S]: the
 // de-interleaving gather is done by the copy engine, lane g of the tile being
 // series g / (G/S), column n2_0 + g % (G/S).
+// exp(-2 pi i m / N) for an exact integer m, rounded once from float64.
+BBT_DEV cf unit_root(long long m, long long N) {
+  double sn, cs;
+  sincospi_d(-2. * (double)(m & (N - 1)) / (double)N, &sn, &cs);
+  return mk((float)cs, (float)sn);
+}
+
 struct DdColTma {
+  int fast_tw;      // twiddle ramps from per-CTA tables (needs G % S == 0)
   int n_boxes;      // copies per tile
   int box_rows;     // rows per copy
   int tn;           // planar source: n2 values per series in a tile (G / S)
+  int stagger_ns;   // delay of every other CTA, so that the CTAs sharing an SM
+                    // run out of phase (one in its butterflies while the
+                    // other exchanges and stores)
 };
 
 template <class C, bool INVERSE>
@@ -690,6 +701,17 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   constexpr size_t kBuf = C::SMEM_BYTES / sizeof(cf) > kTile
                               ? C::SMEM_BYTES / sizeof(cf) : kTile;
   Mbar* bar = reinterpret_cast<Mbar*>(smem + kBuf);
+  // Twiddle tables behind the barrier: the ramp of column n2 = n2_0 + j is
+  //   W_N^{n2 (t + T e)} = [W^{n2_0 t} W^{j t}] [W^{n2_0 T} W^{j T}]^e,
+  // whose second factors do not depend on the tile (W^{j t}: one value per
+  // thread, kept in registers; W^{j T 2^b}: tab_d[b][g]) and whose first
+  // factors are the same for all lanes (tab_a[t], tab_c[b]: computed per tile
+  // by a few threads, one tile ahead).  All are rounded once from float64,
+  // so the threads do no divergent table look-ups at all.
+  constexpr int LE = C::LOG2E > 0 ? C::LOG2E : 1;
+  cf* tab_d = reinterpret_cast<cf*>(bar + 2);       // [LE][G]
+  cf* tab_a = tab_d + LE * C::G;                    // [2][T]
+  cf* tab_c = tab_a + 2 * C::T;                     // [2][8]
   const unsigned N2 = (unsigned)(a.N >> a.log2n1);
   const unsigned S = (unsigned)a.S;
   const unsigned n2s = N2 * S;
@@ -698,6 +720,26 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   const int tid = threadIdx.x;
   const int g = tid % C::G, t = tid / C::G;
   const bool planar_src = INVERSE && a.planar;
+  // Column offset of lane g within its tile.
+  auto lane_j = [&](int lane) -> long long {
+    return planar_src ? lane % m.tn : lane / (int)S;
+  };
+  auto tile_tables = [&](unsigned lin, unsigned slot) {   // threads < T + LE
+    const unsigned frame = lin / nblk;
+    const long long n20 = (long long)((lin - frame * nblk) * C::G) / S;
+    if (tid < C::T)
+      tab_a[slot * C::T + tid] = unit_root(n20 * tid, a.N);
+    else if (tid < C::T + LE)
+      tab_c[slot * 8 + (tid - C::T)] =
+          unit_root((n20 * C::T) << (tid - C::T), a.N);
+  };
+  cf w_jt = mk(1.f, 0.f);
+  if (m.fast_tw) {
+    w_jt = unit_root(lane_j(g) * t, a.N);
+    for (int i = tid; i < LE * C::G; i += C::THREADS)
+      tab_d[i] = unit_root((lane_j(i % C::G) * C::T) << (i / C::G), a.N);
+    if (blockIdx.x < n_tiles) tile_tables(blockIdx.x, 0);
+  }
   auto issue = [&](unsigned lin) {                  // one thread
     const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
     fence_proxy_async();
@@ -726,6 +768,9 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (tid == 0) mbar_init(bar, 1);
   BBT_SYNC();
   if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x);
+#if defined(__CUDA_ARCH__)
+  if (m.stagger_ns > 0 && (blockIdx.x & 1)) __nanosleep(m.stagger_ns);
+#endif
   unsigned k = 0;
 #pragma unroll 1
   for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
@@ -751,14 +796,28 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       for (int e = 0; e < C::E; ++e) v[e] = land[(size_t)e * C::T * C::G];
     }
     BBT_SYNC();  // the landing zone becomes the exchange buffer
-    if (INVERSE && valid) col_twiddle<C, 0>(v, a.big, (int)n2, t, a.scale);
+    if (m.fast_tw && next < n_tiles) tile_tables(next, (k + 1) & 1u);
+    auto twiddle = [&](float scale) {
+      if (m.fast_tw) {
+        cf pw[LE];
+#pragma unroll
+        for (int b = 0; b < C::LOG2E; ++b)
+          pw[b] = cmul(tab_c[(k & 1u) * 8 + b], tab_d[b * C::G + g]);
+        const cf base =
+            cscale(cmul(tab_a[(k & 1u) * C::T + t], w_jt), scale);
+        Ramp<C::LOG2E, 0>::run(v, base, pw);
+      } else {
+        col_twiddle<C, 0>(v, a.big, (int)n2, t, scale);
+      }
+    };
+    if (INVERSE && valid) twiddle(a.scale);
     SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
     block_fft_head<C>(v, t, a.tw1, sm);
     if (tid == 0 && next < n_tiles) issue(next);
     block_fft_tail<C>(v, t, a.tw1, sm);
     if (!valid) continue;
     if (!INVERSE) {
-      col_twiddle<C, 0>(v, a.big, (int)n2, t, 1.f);
+      twiddle(1.f);
       cf* dst = a.work + (long long)frame * a.N * a.S;
       long long step;
       if (a.planar) {
