@@ -23,6 +23,8 @@ struct bbt_dedisperse_plan {
 namespace {
 
 constexpr int kColThreads = 512;
+constexpr int64_t kMaxFramesPerLaunch = 65535;  // the frame goes in grid.y
+constexpr int64_t kCounterBytes = 256;
 
 // Elements per thread of the column FFTs.  HALF: 256-thread CTAs with half
 // the lanes (64 KB tiles, two CTAs per SM).
@@ -80,7 +82,14 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
   constexpr int LE = C::LOG2E > 0 ? C::LOG2E : 1;
   const size_t smem = (C::SMEM_BYTES > kTile ? C::SMEM_BYTES : kTile) +
                       2 * sizeof(Mbar) +
-                      (LE * C::G + 2 * C::T + 16) * sizeof(cf);
+                      (LE * C::G + 2 * C::T + 16 + 2) * sizeof(cf);
+  // Tile counter of this pass, behind the frames in the work buffer.
+  m.next_tile = reinterpret_cast<unsigned*>(
+                    reinterpret_cast<char*>(a.work) +
+                    n_frames * a.N * a.S * (int64_t)sizeof(cf)) +
+                (inverse ? 16 : 0);
+  if (dev_zero(m.next_tile, sizeof(unsigned), st))
+    return fail(BBT_ECUDA, "cannot reset the tile counter");
   m.fast_tw = (C::G % S == 0 || planar_src) && tune("col_fast_tw", 1);
   const int64_t tiles = ceil_div(n2s, C::G) * n_frames;
   const int per_sm = C::THREADS <= 256 ? 2 : 1;
@@ -153,7 +162,9 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
     if (a.tw_sub) {   // the plan stored its chirp for dd_row2_kernel
       if (reinterpret_cast<uintptr_t>(a.work) & 15)
         return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
-      const size_t smem = Row2Cfg<C>::kSmemBytes;
+      const size_t smem = Row2Cfg<C>::kSmemBytes + 16;
+      if (dev_zero(a.row_tile, sizeof(unsigned), st))
+        return fail(BBT_ECUDA, "cannot reset the tile counter");
       auto kern = dd_row2_kernel<C>;
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
@@ -167,7 +178,9 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   if constexpr (PLANAR && !HALF) {
     // Persistent CTAs fed by bulk copies (one tile = one contiguous range).
     if (tune("row_tma", 1) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
-      const size_t smem = C::SMEM_BYTES + sizeof(Mbar);
+      const size_t smem = C::SMEM_BYTES + sizeof(Mbar) + 16;
+      if (dev_zero(a.row_tile, sizeof(unsigned), st))
+        return fail(BBT_ECUDA, "cannot reset the tile counter");
       auto kern = dd_row_tma_kernel<C>;
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
@@ -411,13 +424,14 @@ int bbt_dedisperse_plan_get_response(const bbt_dedisperse_plan* p,
 int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* p,
                                   int64_t n_frames) {
   if (!p || p->log2n1 == 0) return 0;
-  return n_frames * p->n * p->n_series * (int64_t)sizeof(cf);
+  // Frames x points, and behind them the tile counters of the persistent
+  // column passes (one per pass).
+  return std::min<int64_t>(n_frames, kMaxFramesPerLaunch) * p->n *
+             p->n_series * (int64_t)sizeof(cf) + kCounterBytes;
 }
 
 }  // extern "C"
 
-// Frames per launch: the column kernels put the frame in grid.y.
-static const int64_t kMaxFramesPerLaunch = 65535;
 
 static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
                                int64_t in_frame_stride, int64_t n_frames,
@@ -462,6 +476,12 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.tw = p->tw2;
   a.tw1 = p->tw1;
   a.tw_sub = p->tw_sub;
+  // Tile counters sit behind the frames in the work buffer.
+  a.row_tile = work ? reinterpret_cast<unsigned*>(
+                          static_cast<char*>(work) +
+                          n_frames * p->n * p->n_series * (int64_t)sizeof(cf)) +
+                          32
+                    : nullptr;
   a.big = BigTwiddle{p->big_lo, p->big_hi};
   a.chirp = p->chirp;
   a.series_map = p->series_map;

@@ -71,6 +71,12 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
   // Sub-streams per bin so that the grid fills the GPU a few times over.
   const int64_t want = (int64_t)sm_count() * 4 * units;
   int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));
+  // Whole tiles of sub-streams: a CTA of the bulk-copy kernel takes
+  // units / M adjacent spectra at a time.
+  if (INTEGRATE && a.M <= units && units % a.M == 0) {
+    const int64_t nj = units / a.M;
+    msub = ceil_div(msub, nj) * nj;
+  }
   if (msub > max_width) msub = max_width;
   // In-kernel averaging divides every partial sum: keep one per bin.
   if (msub < 1 || (INTEGRATE && a.average)) msub = 1;

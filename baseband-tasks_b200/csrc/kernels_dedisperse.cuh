@@ -32,6 +32,7 @@ struct DdArgs {
   const cf* tw;         // N2-th roots of unity (row FFTs, single-pass frames)
   const cf* tw1;        // N1-th roots of unity (column FFTs)
   const cf* tw_sub;     // (N2/32)-th roots of unity (dd_row2_kernel)
+  unsigned* row_tile;   // device counter handing out the row tiles in order
   BigTwiddle big;       // W_N^m
   const cf* chirp;      // [n_chirp][N1][N2]
   const int* series_map;  // series -> chirp index
@@ -432,11 +433,17 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
     return (left < (unsigned)C::G ? left : (unsigned)C::G) * C::N *
            (unsigned)sizeof(cf);
   };
-  if (tid == 0) mbar_init(bar, 1);
+  // Tiles are drawn from a counter, in order (see DdColTma::next_tile): the
+  // CTAs that run together keep working on the same chirp rows.
+  unsigned* tile_slot = reinterpret_cast<unsigned*>(bar + 1);   // [2]
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    tile_slot[0] = atomic_add(a.row_tile, 1u);
+  }
   BBT_SYNC();
-  if (tid == 0 && blockIdx.x < n_tiles) {
+  if (tid == 0 && tile_slot[0] < n_tiles) {
     unsigned rho0;
-    const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
+    const char* src = reinterpret_cast<const char*>(tile_base(tile_slot[0], rho0));
     const unsigned bytes = tile_bytes(rho0);
     mbar_expect_tx(bar, bytes);
     char* dst = reinterpret_cast<char*>(smem);
@@ -446,7 +453,12 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
   }
   unsigned k = 0;
 #pragma unroll 1
-  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+  for (;; ++k) {
+    const unsigned lin = tile_slot[k & 1u];
+    if (lin >= n_tiles) break;
+    if (tid == 0) tile_slot[(k + 1) & 1u] = atomic_add(a.row_tile, 1u);
+    BBT_SYNC();
+    const unsigned next = tile_slot[(k + 1) & 1u];
     unsigned rho0;
     cf* row = tile_base(lin, rho0) + (long long)g * C::N;
     const unsigned rho = rho0 + g;
@@ -460,7 +472,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
         bulk_prefetch_l2(reinterpret_cast<const char*>(chirp) + o,
                          C::N * sizeof(cf) - o < kChunk
                              ? (unsigned)(C::N * sizeof(cf)) - o : kChunk);
-    const unsigned next = lin + gridDim.x;
     const char* next_src = nullptr;
     unsigned next_bytes = 0;
     if (next < n_tiles) {
@@ -620,11 +631,17 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
     return (left < (unsigned)C::G ? left : (unsigned)C::G) * C::N *
            (unsigned)sizeof(cf);
   };
-  if (tid == 0) mbar_init(bar, 1);
+  // Tiles are drawn from a counter, in order (see DdColTma::next_tile): the
+  // CTAs that run together keep working on the same chirp rows.
+  unsigned* tile_slot = reinterpret_cast<unsigned*>(bar + 1);   // [2]
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    tile_slot[0] = atomic_add(a.row_tile, 1u);
+  }
   BBT_SYNC();
-  if (tid == 0 && blockIdx.x < n_tiles) {
+  if (tid == 0 && tile_slot[0] < n_tiles) {
     unsigned rho0;
-    const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
+    const char* src = reinterpret_cast<const char*>(tile_base(tile_slot[0], rho0));
     const unsigned bytes = tile_bytes(rho0);
     mbar_expect_tx(bar, bytes);
     char* dst = reinterpret_cast<char*>(smem);
@@ -634,7 +651,12 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
   }
   unsigned k = 0;
 #pragma unroll 1
-  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+  for (;; ++k) {
+    const unsigned lin = tile_slot[k & 1u];
+    if (lin >= n_tiles) break;
+    if (tid == 0) tile_slot[(k + 1) & 1u] = atomic_add(a.row_tile, 1u);
+    BBT_SYNC();
+    const unsigned next = tile_slot[(k + 1) & 1u];
     unsigned rho0;
     cf* row = tile_base(lin, rho0) + (long long)g * C::N;
     const unsigned rho = rho0 + g;
@@ -647,7 +669,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
         bulk_prefetch_l2(reinterpret_cast<const char*>(chirp) + o,
                          C::N * sizeof(cf) - o < kChunk
                              ? (unsigned)(C::N * sizeof(cf)) - o : kChunk);
-    const unsigned next = lin + gridDim.x;
     const char* next_src = nullptr;
     unsigned next_bytes = 0;
     if (next < n_tiles) {
@@ -682,6 +703,11 @@ BBT_DEV cf unit_root(long long m, long long N) {
 }
 
 struct DdColTma {
+  unsigned* next_tile;  // device counter (zeroed before the launch): tiles are
+                        // handed out in order, so the tiles in flight stay
+                        // neighbours in memory however the CTAs drift apart
+                        // (with a fixed tile-to-CTA map the column passes
+                        // lost 15-25 % of their speed on long launches)
   int fast_tw;      // twiddle ramps from per-CTA tables (needs G % S == 0)
   int n_boxes;      // copies per tile
   int box_rows;     // rows per copy
@@ -712,6 +738,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   cf* tab_d = reinterpret_cast<cf*>(bar + 2);       // [LE][G]
   cf* tab_a = tab_d + LE * C::G;                    // [2][T]
   cf* tab_c = tab_a + 2 * C::T;                     // [2][8]
+  unsigned* tile_slot = reinterpret_cast<unsigned*>(tab_c + 16);  // [2]
   const unsigned N2 = (unsigned)(a.N >> a.log2n1);
   const unsigned S = (unsigned)a.S;
   const unsigned n2s = N2 * S;
@@ -738,7 +765,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     w_jt = unit_root(lane_j(g) * t, a.N);
     for (int i = tid; i < LE * C::G; i += C::THREADS)
       tab_d[i] = unit_root((lane_j(i % C::G) * C::T) << (i / C::G), a.N);
-    if (blockIdx.x < n_tiles) tile_tables(blockIdx.x, 0);
   }
   auto issue = [&](unsigned lin) {                  // one thread
     const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
@@ -765,15 +791,26 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
         tensor_prefetch_3d(&map, (int)c0, q * m.box_rows, (int)frame);
     }
   };
-  if (tid == 0) mbar_init(bar, 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    tile_slot[0] = atomic_add(m.next_tile, 1u);
+  }
   BBT_SYNC();
-  if (tid == 0 && blockIdx.x < n_tiles) issue(blockIdx.x);
-#if defined(__CUDA_ARCH__)
-  if (m.stagger_ns > 0 && (blockIdx.x & 1)) __nanosleep(m.stagger_ns);
-#endif
+  if (m.fast_tw && tile_slot[0] < n_tiles) tile_tables(tile_slot[0], 0);
+  if (tid == 0 && tile_slot[0] < n_tiles) issue(tile_slot[0]);
   unsigned k = 0;
 #pragma unroll 1
-  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+  for (;; ++k) {
+    const unsigned lin = tile_slot[k & 1u];
+    if (lin >= n_tiles) break;
+    // Thread 0 draws the next tile now and passes it on through shared
+    // memory (read after the next barrier).
+    unsigned next = 0;
+    if (tid == 0) {
+      next = atomic_add(m.next_tile, 1u);
+      tile_slot[(k + 1) & 1u] = next;
+      if (next < n_tiles) prefetch(next);
+    }
     const unsigned frame = lin / nblk, c0 = (lin - frame * nblk) * C::G;
     // Flat column n2*S + s of this lane.
     unsigned n2, sser;
@@ -786,8 +823,6 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       sser = col - n2 * S;
     }
     const bool valid = n2 < N2 && sser < S;
-    const unsigned next = lin + gridDim.x;
-    if (tid == 32 && next < n_tiles) prefetch(next);
     mbar_wait(bar, k & 1u, k);
     cf v[C::E];
     {
@@ -796,7 +831,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       for (int e = 0; e < C::E; ++e) v[e] = land[(size_t)e * C::T * C::G];
     }
     BBT_SYNC();  // the landing zone becomes the exchange buffer
-    if (m.fast_tw && next < n_tiles) tile_tables(next, (k + 1) & 1u);
+    if (m.fast_tw && tile_slot[(k + 1) & 1u] < n_tiles)
+      tile_tables(tile_slot[(k + 1) & 1u], (k + 1) & 1u);
     auto twiddle = [&](float scale) {
       if (m.fast_tw) {
         cf pw[LE];

@@ -60,6 +60,9 @@ inline unsigned long long atomic_add(unsigned long long* p,
                                      unsigned long long v) {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+inline unsigned atomic_add(unsigned* p, unsigned v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
 }  // namespace bbt
 float* bbt_emu_scratch();
 namespace bbt {
@@ -133,6 +136,9 @@ __device__ __forceinline__ float atomic_add(float* p, float v) {
 }
 __device__ __forceinline__ unsigned long long atomic_add(
     unsigned long long* p, unsigned long long v) {
+  return atomicAdd(p, v);
+}
+__device__ __forceinline__ unsigned atomic_add(unsigned* p, unsigned v) {
   return atomicAdd(p, v);
 }
 __device__ __forceinline__ void sincospi_d(double x, double* s, double* c) {

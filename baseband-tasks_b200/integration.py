@@ -266,17 +266,21 @@ class Integrate(BaseTaskBase):
     def _frame_dependent(self):
         return False
 
-    def read_sums(self, count=None):
+    def read_sums(self, count=None, within=None):
         """Sums and counts of the next ``count`` output samples, on the device.
 
         Returns ``(sums, counts)``: float32 sums with the shape of the output
         samples (complex streams as real, imaginary pairs in the last axis)
         and int64 counts per bin.  This is what is reduced over ranks when a
-        stream is sharded in time (`baseband_tasks_b200.parallel`).
+        stream is sharded in time (`baseband_tasks_b200.parallel`): with
+        ``within=(first, last)`` only the samples ``[first, last)`` of the
+        underlying stream are read, so a rank holding a block of the stream
+        gets partial sums and counts for the bins its block cuts through.
         """
         count = self._check_read(count, None)
         a = self.offset
         saved, self._raw_sums = getattr(self, '_raw_sums', False), True
+        self._within = within
         try:
             if self._frame_dependent():
                 parts = []
@@ -292,8 +296,18 @@ class Integrate(BaseTaskBase):
                 sums, cnts = self._integrate_samples(a, count)
         finally:
             self._raw_sums = saved
+            self._within = None
         self.offset = a + count
         return sums, cnts
+
+    _within = None
+
+    def _clip(self, start, stop):
+        """Upstream range to read, restricted to ``within`` of `read_sums`."""
+        if self._within is not None:
+            start = max(start, int(self._within[0]))
+            stop = min(stop, int(self._within[1]))
+        return start, stop
 
     def _integrate_samples(self, sample0, n_sample):
         """Output samples [sample0, sample0 + n_sample)."""
@@ -353,19 +367,22 @@ class Integrate(BaseTaskBase):
         lib = _cabi.lib()
         d_off = B.as_device(offsets)
         n_bins = len(offsets) - 1
-        start, stop = int(offsets[0]), int(offsets[-1])
+        start, stop = self._clip(int(offsets[0]), int(offsets[-1]))
         ratio = self._src_ratio
         src = self._src
-        per_sample = (int(np.prod(src.sample_shape, dtype=np.int64))
-                      * np.dtype(src.dtype).itemsize * ratio)
-        chunk = max(1, _base.BLOCK_BYTES // max(per_sample, 1))
-        # Prefer chunks aligned with the frames of the source.
-        src_spf = max(1, getattr(src, 'samples_per_frame', 1) // ratio)
-        if chunk > src_spf:
-            chunk = (chunk // src_spf) * src_spf
+        per_src_sample = (int(np.prod(src.sample_shape, dtype=np.int64))
+                          * np.dtype(src.dtype).itemsize)
+        # Chunks are whole runs of frames of the source (so that it computes
+        # every frame once): boundaries at multiples of ``chunk_src`` source
+        # samples, rounded down to whole samples of ``ih``.
+        src_frame = max(1, getattr(src, 'samples_per_frame', 1))
+        chunk_src = src_frame * max(1, _base.BLOCK_BYTES
+                                    // max(per_src_sample * src_frame, 1))
+        chunk_src = max(chunk_src, ratio)
         pos = start
         while pos < stop:
-            nxt = min(stop, (pos // chunk + 1) * chunk)
+            nxt = ((pos * ratio) // chunk_src + 1) * chunk_src // ratio
+            nxt = min(stop, max(nxt, pos + 1))
             n = nxt - pos
             src.seek(pos * ratio)
             if hasattr(src, 'read_device'):
@@ -482,7 +499,7 @@ class Fold(Integrate):
     def _fold(self, offsets, lo, hi, inner, sums, count):
         lib = _cabi.lib()
         d_lo, d_hi = B.as_device(lo), B.as_device(hi)
-        start, stop = int(offsets[0]), int(offsets[-1])
+        start, stop = self._clip(int(offsets[0]), int(offsets[-1]))
         src = self._src
         ih = self.ih
         per_sample = (int(np.prod(src.sample_shape, dtype=np.int64))

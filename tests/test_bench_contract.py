@@ -24,7 +24,10 @@ def run_bench(*args, timeout=900):
 
 
 def test_reference_arm_line():
-    line = run_bench('--impl', 'reference', '--steps', '1', '--warmup', '0')
+    # C2 frames (2^20 points x 16 series) keep the CPU test short; the default
+    # workload (C4, 2^24-point frames) runs the same code.
+    line = run_bench('--impl', 'reference', '--steps', '1', '--warmup', '0',
+                     '--workload', 'C2')
     assert line['impl'] == 'reference'
     assert BASE_KEYS <= set(line)
     assert E2E_KEYS <= set(line['e2e'])
@@ -34,6 +37,19 @@ def test_reference_arm_line():
     assert cpu['kind'] in ('port', 'reference') and cpu['cores'] >= 1
     assert cpu['value'] == line['value'] and cpu['sample']
     assert line['config']['workload'].startswith('C2')
+
+
+def test_default_workload_is_the_target_config():
+    """The driver's plain run measures configs[3] (C4), with identical
+    ``config`` objects in both arms."""
+    sys.path.insert(0, ROOT)
+    import bench
+    ap_default = 'C4'
+    assert bench.WORKLOADS[ap_default]['log2n'] == 24
+    cfg = bench.config_of('C4', bench.WORKLOADS['C4'])
+    assert cfg['workload'].startswith('C4') and cfg['fft_length'] == 1 << 24
+    import inspect
+    assert "default='C4'" in inspect.getsource(bench.main)
 
 
 @pytest.mark.gpu
@@ -50,4 +66,5 @@ def test_b200_arm_line():
     assert roof['bound'] == 'hbm' and 0 < roof['frac'] < 1
     assert abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-9
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(line['clocks'])
-    assert line['config']['workload'].startswith('C2')
+    assert line['config']['workload'].startswith('C4')
+    assert line['strong']['value'] > 0

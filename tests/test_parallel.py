@@ -126,3 +126,101 @@ def test_fold_sharded_over_two_ranks(tmp_path):
         np.testing.assert_allclose(r[0]['avg'],
                                    r[0]['sums'] / r[0]['counts'][..., None],
                                    rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# Dedisperse -> Channelize -> Power -> Integrate, shared out in time: every
+# rank builds the chain on its own block of the stream (parallel.StreamBlock),
+# integrates the bins its block touches and the bins cut by a rank boundary
+# are completed with one small all-reduce.
+N_CHAN, STEP = 32, 17      # 17 spectra per bin: boundaries fall mid-bin
+
+
+def _chain_integrate(bt, src):
+    dd = bt.Dedisperse(src, DM, samples_per_frame=SPF)
+    return dd, bt.Integrate(bt.Power(bt.Channelize(dd, N_CHAN)), STEP,
+                            average=False)
+
+
+def _worker_integrate(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    bt = _setup()
+    from baseband_tasks_b200 import parallel
+    assert parallel.init('gloo') == (rank, world)
+    x = _data()
+    whole = _source(bt, x)
+    probe, _ = _chain_integrate(bt, whole)
+    pad = probe._ih_samples_per_frame - SPF
+    n_frames = (N - pad) // SPF
+    plans = [parallel.block_plan(n_frames, SPF, pad, N_CHAN, r, world)
+             for r in range(world)]
+    first, last, in0, in1 = plans[rank]
+    # Only this rank's block of the stream is handed to its chain.
+    block = parallel.StreamBlock(
+        x[in0:in1].copy(), in0, N, whole.start_time, RATE,
+        samples_per_frame=1000, frequency=300e6, sideband=1,
+        polarization=np.array(['X', 'Y']))
+    dd, it = _chain_integrate(bt, block)
+    assert it.shape == _chain_integrate(bt, whole)[1].shape
+    edges = it._get_offsets(np.arange(it.shape[0] + 1))
+    bins = [parallel.bin_range(edges, p[0] // N_CHAN, p[1] // N_CHAN)
+            for p in plans]
+    b0, b1 = bins[rank]
+    it.seek(b0)
+    sums, counts = it.read_sums(b1 - b0, within=(first // N_CHAN,
+                                                 last // N_CHAN))
+    parallel.reduce_edge_bins(sums, counts, bins[rank], bins)
+    # Reading outside the block fails loudly.
+    if world > 1:
+        other = plans[1 - rank]
+        try:
+            block.seek(other[2] if rank else other[3] - 1)
+            block.read(1)
+            raised = False
+        except EOFError:
+            raised = True
+        assert raised
+    np.savez(os.path.join(out_dir, f'int{rank}.npz'), sums=sums.numpy(),
+             counts=counts.numpy(), bins=np.array([b0, b1]),
+             plan=np.array(plans[rank]))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_integrate_chain_sharded_over_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    import backend
+    backend.build_emu()
+    world = 2
+    port = 29500 + (os.getpid() + 7) % 1000
+    mp.spawn(_worker_integrate, args=(world, port, str(tmp_path)),
+             nprocs=world, join=True)
+    r = [np.load(tmp_path / f'int{i}.npz') for i in range(world)]
+    bt = _setup()
+    whole = _source(bt, _data())
+    _, it = _chain_integrate(bt, whole)
+    n_units = r[1]['plan'][1] // N_CHAN         # spectra in complete frames
+    ref = it.read()
+    # The ranks' ranges tile the output, cut inside a bin.
+    assert r[0]['plan'][1] == r[1]['plan'][0] and r[0]['plan'][0] == 0
+    assert r[0]['bins'][1] - 1 == r[1]['bins'][0]
+    for i in range(world):
+        b0, b1 = r[i]['bins']
+        want = ref[b0:b1]
+        # Bins that lie wholly in complete frames are identical to the
+        # single-process result; the last may be cut by the end of the
+        # complete frames.
+        edges = it._get_offsets(np.arange(it.shape[0] + 1))
+        full = edges[b0 + 1:b1 + 1] <= n_units
+        np.testing.assert_array_equal(
+            r[i]['counts'][full], want['count'][full][:, 0, 0])
+        np.testing.assert_allclose(
+            r[i]['sums'][full].reshape(want['data'][full].shape),
+            want['data'][full], rtol=1e-5,
+            atol=1e-5 * np.abs(want['data']).max())
+    # Both ranks hold the completed shared bin.
+    np.testing.assert_array_equal(r[0]['counts'][-1], r[1]['counts'][0])
+    np.testing.assert_allclose(r[0]['sums'][-1], r[1]['sums'][0], rtol=1e-6)

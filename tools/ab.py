@@ -69,6 +69,7 @@ def main():
     wl = sys.argv[1]
     variants = sys.argv[2:] or ['base']
     N, S, frames, pad_start, pad_end, n_chirp = SHAPES[wl]
+    frames = int(os.environ.get('AB_FRAMES', frames))
     spf = N - pad_start - pad_end
     n_in = spf * (frames - 1) + N
     g = torch.Generator(device=dev).manual_seed(1)
@@ -120,7 +121,10 @@ def main():
         step()
         torch.cuda.synchronize()
         got = (out.clone(), sums.clone(), cnt.clone())
-        times = profile(step, 5)
+        reps = int(os.environ.get('AB_REPS', 5))
+        for _ in range(int(os.environ.get('AB_SOAK', 0))):
+            step()
+        times = profile(step, reps)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
