@@ -162,9 +162,7 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
     if (a.tw_sub) {   // the plan stored its chirp for dd_row2_kernel
       if (reinterpret_cast<uintptr_t>(a.work) & 15)
         return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
-      const size_t smem = Row2Cfg<C>::kSmemBytes + 16;
-      if (dev_zero(a.row_tile, sizeof(unsigned), st))
-        return fail(BBT_ECUDA, "cannot reset the tile counter");
+      const size_t smem = Row2Cfg<C>::kSmemBytes;
       auto kern = dd_row2_kernel<C>;
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
@@ -178,9 +176,7 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   if constexpr (PLANAR && !HALF) {
     // Persistent CTAs fed by bulk copies (one tile = one contiguous range).
     if (tune("row_tma", 1) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
-      const size_t smem = C::SMEM_BYTES + sizeof(Mbar) + 16;
-      if (dev_zero(a.row_tile, sizeof(unsigned), st))
-        return fail(BBT_ECUDA, "cannot reset the tile counter");
+      const size_t smem = C::SMEM_BYTES + sizeof(Mbar);
       auto kern = dd_row_tma_kernel<C>;
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
@@ -476,12 +472,6 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.tw = p->tw2;
   a.tw1 = p->tw1;
   a.tw_sub = p->tw_sub;
-  // Tile counters sit behind the frames in the work buffer.
-  a.row_tile = work ? reinterpret_cast<unsigned*>(
-                          static_cast<char*>(work) +
-                          n_frames * p->n * p->n_series * (int64_t)sizeof(cf)) +
-                          32
-                    : nullptr;
   a.big = BigTwiddle{p->big_lo, p->big_hi};
   a.chirp = p->chirp;
   a.series_map = p->series_map;
