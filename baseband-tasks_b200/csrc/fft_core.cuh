@@ -342,7 +342,45 @@ struct FftCfg {
   static constexpr int NPAD = N + (N >> PADSHIFT);  // exchange slots per FFT
   static constexpr size_t SMEM_BYTES =
       Plan::NS > 1 ? (size_t)G * NPAD * sizeof(float) * 2 : 16;
+  // Gathered twiddle tables (apply_twiddles_tab): three runs of Ns entries
+  // for every stage after the first; offset of the stage that starts with
+  // 2^LOG2NS points combined, and the total.
+  template <int LOG2NS>
+  static BBT_HD constexpr int twtab_offset() {
+    int off = 0;
+    for (int s = 1; s < Plan::NS; ++s) {
+      if (Plan::before(s) == LOG2NS) return off;
+      off += 3 << Plan::before(s);
+    }
+    return off;
+  }
+  static BBT_HD constexpr int twtab_size() {
+    int off = 0;
+    for (int s = 1; s < Plan::NS; ++s) off += 3 << Plan::before(s);
+    return off > 0 ? off : 1;
+  }
 };
+
+// Fill the gathered twiddle tables of a transform from its table of N-th
+// roots of unity (all threads of the group take part; synchronise after).
+template <class C>
+BBT_HD void fill_twtab(cf* tab, const cf* tw, int tid, int nthreads) {
+  using P = typename C::Plan;
+  int off = 0;
+  for (int s = 1; s < P::NS; ++s) {
+    const int ns = 1 << P::before(s);
+    const int shift = C::LOG2N - P::before(s) - P::bits(s);
+    for (int i = tid; i < 3 * ns; i += nthreads) {
+      const int which = i / ns, k = i - which * ns;
+      const int mult = which == 0 ? 1 : (which == 1 ? 8 : 16);
+      // Entries a stage of smaller radix never reads may fall outside the
+      // table of roots: leave them alone.
+      const long long idx = (long long)(k << shift) * mult;
+      if (idx < C::N) tab[off + i] = tw[idx];
+    }
+    off += 3 * ns;
+  }
+}
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
 #define BBT_SYNC() __syncthreads()
@@ -378,6 +416,8 @@ struct SmemLaneFast {
   BBT_HD cf& ref(int s) const { return base[s * G + g]; }
   BBT_HD cf& at(int p) const { return ref(slot(p)); }
   static BBT_HD void sync() { BBT_SYNC(); }
+  static constexpr bool kTwTab = false;
+  const cf* twtab = nullptr;
 };
 template <int PADSHIFT>
 struct SmemLaneSlow {
@@ -387,6 +427,8 @@ struct SmemLaneSlow {
   BBT_HD cf& ref(int s) const { return base[s]; }
   BBT_HD cf& at(int p) const { return ref(slot(p)); }
   static BBT_HD void sync() { BBT_SYNC(); }
+  static constexpr bool kTwTab = false;
+  const cf* twtab = nullptr;
 };
 // A transform whose threads all belong to one warp (at most 32 x E points):
 // exchanges need only a warp-level barrier, so the warps of a CTA run their
@@ -399,6 +441,9 @@ struct SmemWarp {
   BBT_HD cf& ref(int s) const { return base[s]; }
   BBT_HD cf& at(int p) const { return ref(slot(p)); }
   static BBT_HD void sync() { BBT_SYNCWARP(); }
+  // Stage twiddles from gathered tables in shared memory (fill_twtab).
+  static constexpr bool kTwTab = true;
+  const cf* twtab;
 };
 
 // Streaming access to data that is touched once: do not let it displace the
@@ -468,6 +513,48 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 #endif
 }
 
+// b[r] *= w^r for r < R: w = w1, w^8 = w8 and w^16 = w16 are given (looked up
+// by the caller), w^2 and w^4 come from squaring w (BBT_TW_SQUARE >= 1) and
+// the other powers are products of two of these.
+template <int R>
+BBT_HD void apply_twiddle_powers(cf* b, cf w1, cf w8, cf w16) {
+  if constexpr (R >= 2) {
+    cf w[8];  // w^1 .. w^7
+    w[1] = w1;
+    if constexpr (R >= 4) {
+      w[2] = cmul(w[1], w[1]);
+      w[3] = cmul(w[2], w[1]);
+    }
+    if constexpr (R >= 8) {
+      w[4] = cmul(w[2], w[2]);
+      w[5] = cmul(w[4], w[1]);
+      w[6] = cmul(w[4], w[2]);
+      w[7] = cmul(w[4], w[3]);
+    }
+    constexpr int LOW = R < 8 ? R : 8;
+#pragma unroll
+    for (int r = 1; r < LOW; ++r) b[r] = cmul(b[r], w[r]);
+    if constexpr (R >= 16) {
+      const cf hi = w8;
+      b[8] = cmul(b[8], hi);
+#pragma unroll
+      for (int r = 1; r < 8; ++r) b[8 + r] = cmul(b[8 + r], cmul(hi, w[r]));
+      if constexpr (R >= 32) {
+        const cf hi2 = w16;
+        b[16] = cmul(b[16], hi2);
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          b[16 + r] = cmul(b[16 + r], cmul(hi2, w[r]));
+        cf hi3 = cmul(hi2, hi);
+        b[24] = cmul(b[24], hi3);
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          b[24 + r] = cmul(b[24 + r], cmul(hi3, w[r]));
+      }
+    }
+  }
+}
+
 #ifndef BBT_TW_SQUARE
 // 1: powers of two of the twiddle by squaring instead of look-ups; 2: w^8 and
 // w^16 looked up (less rounding error, two more loads; the default, see
@@ -478,6 +565,13 @@ BBT_HD cf ldtw(const cf* tw, int i) {
 // others are products of two looked-up or derived values.
 template <int R>
 BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
+#if BBT_TW_SQUARE == 2
+  cf w1 = mk(1.f, 0.f), w8 = w1, w16 = w1;
+  if constexpr (R >= 2) w1 = ldtw(tw, kk);
+  if constexpr (R >= 16) w8 = ldtw(tw, 8 * kk);
+  if constexpr (R >= 32) w16 = ldtw(tw, 16 * kk);
+  apply_twiddle_powers<R>(b, w1, w8, w16);
+#else
   if constexpr (R >= 2) {
     cf w[8];  // w^1 .. w^7
     w[1] = ldtw(tw, kk);
@@ -513,6 +607,20 @@ BBT_HD void apply_twiddles(cf* b, const cf* __restrict__ tw, int kk) {
       }
     }
   }
+#endif
+}
+
+// Twiddles of one stage from a table gathered per stage in shared memory
+// (tab[which * Ns + k] = w_k^{1, 8, 16}): consecutive threads read consecutive
+// entries, whereas the strided look-ups tw[8 k], tw[16 k] of consecutive k
+// touch a different cache line each.
+template <int R>
+BBT_HD void apply_twiddles_tab(cf* b, const cf* tab, int ns, int k) {
+  cf w1 = mk(1.f, 0.f), w8 = w1, w16 = w1;
+  if constexpr (R >= 2) w1 = tab[k];
+  if constexpr (R >= 16) w8 = tab[ns + k];
+  if constexpr (R >= 32) w16 = tab[2 * ns + k];
+  apply_twiddle_powers<R>(b, w1, w8, w16);
 }
 
 // One Stockham stage: Ns = 2^LOG2NS points already combined, radix 2^LOG2R.
@@ -530,7 +638,11 @@ BBT_HD void fft_stage(cf* v, int t, const cf* __restrict__ tw, const Smem& sm) {
     for (int r = 0; r < R; ++r) b[r] = v[q + r * NB];
     if constexpr (LOG2NS > 0) {
       // tw is the table of N-th roots of unity: exp(-2 pi i m / N), m < N.
-      apply_twiddles<R>(b, tw, k << (C::LOG2N - LOG2NS - LOG2R));
+      if constexpr (Smem::kTwTab)
+        apply_twiddles_tab<R>(b, sm.twtab + C::template twtab_offset<LOG2NS>(),
+                              Ns, k);
+      else
+        apply_twiddles<R>(b, tw, k << (C::LOG2N - LOG2NS - LOG2R));
     }
     Dft<R>::run(b);
     if constexpr ((1 << (LOG2NS + LOG2R)) == C::N) {

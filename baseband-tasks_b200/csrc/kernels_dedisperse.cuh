@@ -524,7 +524,12 @@ struct Row2Cfg {
   static constexpr size_t kElems =
       (size_t)C::G * 32 * P > C::SMEM_BYTES / sizeof(cf)
           ? (size_t)C::G * 32 * P : C::SMEM_BYTES / sizeof(cf);
-  static constexpr size_t kSmemBytes = kElems * sizeof(cf) + sizeof(Mbar);
+  // Behind the matrix: the barrier and the gathered twiddle tables (outer
+  // twiddles W_N2^{u {1, 8, 16}}, u < M, then those of the sub-transform).
+  static constexpr int kTabOuter = 3 * M;
+  static constexpr size_t kSmemBytes =
+      kElems * sizeof(cf) + 2 * sizeof(Mbar) +
+      (kTabOuter + CS::twtab_size()) * sizeof(cf);
 };
 
 template <class C>
@@ -543,6 +548,8 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   const int k1 = u / Ts, tt = u % Ts;        // sub-transform and place in it
   constexpr unsigned kChunk = 32 * 1024;
   cf* X = smem + (size_t)g * 32 * P;         // this row's [32][P] matrix
+  const cf* tab_outer = reinterpret_cast<const cf*>(bar + 2);
+  const cf* tab_sub = tab_outer + R::kTabOuter;
   mbar_wait(bar, phase & 1u, phase);
   cf v[32];
   {
@@ -553,7 +560,7 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   BBT_SYNC();  // the landing zone becomes the exchange buffer
   // Forward: over e in this thread, twiddle, transpose.
   Dft<32>::run(v);
-  apply_twiddles<32>(v, tw, u);
+  apply_twiddles_tab<32>(v, tab_outer, M, u);
 #pragma unroll
   for (int r = 0; r < 32; ++r) X[r * P + u] = v[r];
   BBT_SYNC();
@@ -562,7 +569,7 @@ BBT_DEV_NOINLINE void dd_row2_tile(
 #pragma unroll
   for (int e = 0; e < 32; ++e) v[e] = mine[tt + Ts * e];
   BBT_SYNCWARP();
-  SmemWarp<CS::PADSHIFT> sw{mine};
+  SmemWarp<CS::PADSHIFT> sw{mine, tab_sub};
   block_fft<CS>(v, tt, tw_sub, sw);
   if (valid) {
 #pragma unroll
@@ -604,6 +611,17 @@ template <class C>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   Mbar* bar = reinterpret_cast<Mbar*>(smem + Row2Cfg<C>::kElems);
+  {
+    // Twiddle tables, gathered once per CTA (see apply_twiddles_tab).
+    using R = Row2Cfg<C>;
+    cf* tab_outer = reinterpret_cast<cf*>(bar + 2);
+    for (int i = threadIdx.x; i < R::kTabOuter; i += C::THREADS) {
+      const int which = i / R::M, u = i - which * R::M;
+      tab_outer[i] = a.tw[u * (which == 0 ? 1 : (which == 1 ? 8 : 16))];
+    }
+    fill_twtab<typename R::CS>(tab_outer + R::kTabOuter, a.tw_sub,
+                               threadIdx.x, C::THREADS);
+  }
   const unsigned n1 = (unsigned)(a.N >> a.log2n2);
   const unsigned S = (unsigned)a.S;
   const unsigned rows = n1 * S;

@@ -327,6 +327,33 @@ class Job:
         return run
 
 
+def bind_near_gpu(local):
+    """Run this process (and allocate its pinned host block) on the NUMA
+    node the GPU hangs off: with eight ranks copying 6.6 GB per step each,
+    host memory on the wrong node halves the PCIe rate.  Returns the node or
+    None when the topology cannot be read."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node'
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist'
+                         ).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -337,6 +364,7 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
+    numa_node = bind_near_gpu(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     lib = _cabi.lib()
@@ -587,7 +615,8 @@ def run_b200(args):
                 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': int(d2h_bytes),
                 'ms_per_step': ms_e2e / args.steps,
-                'h2d_gbs_per_rank': h2d / (ms_e2e / args.steps * 1e-3) / 1e9},
+                'h2d_gbs_per_rank': h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
+                'host_numa_node': numa_node},
         # Supplementary: the same step fed with the block stored as 8-bit
         # (re, im) codes (as recorded baseband data are) and decoded on the
         # device; `e2e` above is the float32 stream BASELINE.json describes.
