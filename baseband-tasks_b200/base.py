@@ -36,36 +36,61 @@ BLOCK_BYTES = 1 << 31
 
 
 def check_broadcast_to(value, sample_shape):
-    """`numpy.broadcast_to` with a clearer error (base.py:24-34)."""
+    """``value`` broadcast (read-only view) to ``sample_shape``.
+
+    Subclasses of ndarray (quantities) are kept.  Raises ValueError, saying
+    what the shape was meant for, if the two are incompatible.
+    """
     try:
-        broadcast = np.broadcast_to(value, sample_shape, subok=True)
+        return np.broadcast_to(value, sample_shape, subok=True)
     except ValueError as exc:
-        exc.args += ("value cannot be broadcast to sample shape",)
-        raise
-    return broadcast
+        raise ValueError(*exc.args, "value cannot be broadcast to sample "
+                         "shape") from None
 
 
 def simplify_shape(value):
-    """Drop axes along which all entries are equal (base.py:37-53)."""
-    for axis in range(value.ndim):
-        value_0 = value[(slice(None),) * axis + (slice(0, 1),)]
-        if value.strides[axis] == 0 or np.all(value == value_0):
-            value = value_0
-    first_not_unity = next((i for (i, s) in enumerate(value.shape)
-                            if s > 1), value.ndim)
-    return value.reshape(value.shape[first_not_unity:]).copy()
+    """The smallest array that broadcasts to the same thing as ``value``.
+
+    Axes along which nothing varies are reduced to length one and leading
+    unit axes are dropped, so that e.g. a frequency per channel stored for a
+    ``(channel, polarization)`` sample has shape ``(n_chan, 1)``.  Returns a
+    copy (never a view of broadcast memory).
+    """
+    value = np.asanyarray(value)
+    for axis, length in enumerate(value.shape):
+        if length == 1:
+            continue
+        head = value.take([0], axis=axis)
+        # A zero stride means a broadcast axis: no need to compare.
+        if value.strides[axis] == 0 or bool((value == head).all()):
+            value = head
+    n_lead = 0
+    while n_lead < value.ndim and value.shape[n_lead] == 1:
+        n_lead += 1
+    return value.reshape(value.shape[n_lead:]).copy()
 
 
 def getattr_if_none(ih, attr, value=None, *, required=True, **kwargs):
-    """`getattr` used only if no value was passed in (base.py:56-84)."""
-    if value is None:
-        value = kwargs.get(attr, None)
-        if value is None:
-            value = getattr(ih, attr, None)
-    if required and value is None:
+    """``value`` if one was given, else ``kwargs[attr]``, else ``ih.attr``.
+
+    With ``required`` (default), TypeError if all three are missing: a task
+    needs e.g. frequencies either from its input stream or from the caller.
+    """
+    for candidate in (value, kwargs.get(attr), getattr(ih, attr, None)):
+        if candidate is not None:
+            return candidate
+    if required:
         raise TypeError(f"{attr!r} should either be defined by the "
                         "underlying stream or passed in.")
-    return value
+    return None
+
+
+def _same(a, b):
+    """Whether two argument values are equal, whatever they are."""
+    try:
+        return bool(np.all(a == b))
+    except Exception:
+        return False
 
 
 def _copy_meta(meta):
@@ -131,22 +156,19 @@ class Base:
 
     # ---------------------------------------------------------------- repr
     def _repr_item(self, key, default, value=None):
-        """``key=value`` for the repr, or None when there is nothing to show:
-        the value is unknown, or equal to the default of the argument."""
-        for name in (key, '_' + key):
-            if value is not None:
-                break
-            value = getattr(self, name, None)
+        """Text for one constructor argument in the repr, or None to leave it
+        out: arguments nothing is known about, and those at their default."""
+        if value is None:
+            # Look under the public name first, then the private one.
+            value = next((v for v in (getattr(self, name, None)
+                                      for name in (key, '_' + key))
+                          if v is not None), None)
         if value is None:
             return None
-        if default is not inspect.Parameter.empty:
-            try:
-                same = bool(np.all(value == default))
-            except Exception:
-                same = False
-            if same:
-                return None
-        return f"{key}={value}".replace('\n', ',')
+        has_default = default is not inspect.Parameter.empty
+        if has_default and _same(value, default):
+            return None
+        return ','.join(f"{key}={value}".splitlines())
 
     def _repr_parameters(self):
         """Constructor arguments of this class and, where it passes
@@ -323,19 +345,23 @@ class Base:
         return data
 
     def _check_read(self, count, out):
+        """Number of samples a `read` is to deliver, after the checks the
+        reference makes (base.py:404-423): closed stream, shape of ``out``,
+        and reading beyond the end (refused before anything is read)."""
         if self.closed:
             raise ValueError("I/O operation on closed stream.")
-        samples_left = self.shape[0] - self.offset
-        if out is None:
-            if count is None or count < 0:
-                count = max(0, samples_left)
-        else:
+        available = max(self.shape[0] - self.offset, 0)
+        if out is not None:
             assert out.shape[1:] == self.sample_shape, (
-                "'out' must have trailing shape {}".format(self.sample_shape))
-            count = out.shape[0]
-        if count > samples_left:
+                f"'out' must have trailing shape {self.sample_shape}")
+            wanted = out.shape[0]
+        elif count is None or count < 0:
+            wanted = available
+        else:
+            wanted = count
+        if wanted > available:
             raise EOFError("cannot read from beyond end of input.")
-        return count
+        return wanted
 
     def _read_data(self, count, out=None):
         """Samples [offset, offset+count) from cached frames (base.py:425-438).
@@ -362,13 +388,16 @@ class Base:
         return result
 
     def _get_frame(self, offset):
-        """Frame holding ``offset`` and the offset in it (base.py:440-467)."""
-        frame_index, sample_offset = divmod(offset, self.samples_per_frame)
-        if frame_index != self._frame_index:
-            self.offset = frame_index * self.samples_per_frame
-            self._frame = self._read_frame(frame_index)
-            self._frame_index = frame_index
-        return self._frame, sample_offset
+        """The frame that holds sample ``offset`` and the position of that
+        sample in it.  One frame is kept: it is produced (with the sample
+        pointer at its start, as sources expect) only when another one is
+        asked for."""
+        spf = self.samples_per_frame
+        wanted = offset // spf
+        if self._frame_index != wanted:
+            self.offset = wanted * spf
+            self._frame, self._frame_index = self._read_frame(wanted), wanted
+        return self._frame, offset - wanted * spf
 
     def __getitem__(self, item):
         from .shaping import GetSlice
@@ -435,16 +464,14 @@ class BaseTaskBase(Base):
         super().__init__(**inherited, **kwargs)
 
     def _repr_item(self, key, default, value=None):
-        if key == 'ih':          # shown once, indented, below the arguments
-            return 'ih'
+        if key == 'ih':
+            return 'ih'          # the input is shown once, below the arguments
         if default is None:
-            # Arguments left at what the input provides are not repeated.
-            if key == 'samples_per_frame':
-                default = self._ih_samples_per_frame
-            elif key == 'ih_samples_per_frame':
-                default = self.ih.samples_per_frame
-            else:
-                default = getattr(self.ih, key, None)
+            # "Take it from the input" is the default: what the input has is
+            # then what the argument defaults to, and is not repeated.
+            inherited = {'samples_per_frame': self._ih_samples_per_frame,
+                         'ih_samples_per_frame': self.ih.samples_per_frame}
+            default = inherited.get(key, getattr(self.ih, key, None))
         return super()._repr_item(key, default=default, value=value)
 
     def __repr__(self):
@@ -693,9 +720,9 @@ class Task(TaskBase):
         return len(params) == 2
 
     def _repr_item(self, key, default, value=None):
-        # Show the function itself, not the bound method made from it.
-        if key == 'task' and isinstance(self.task, types.MethodType):
-            value = self.task.__func__
+        if key == 'task':
+            # The callable as it was passed in, not the method bound from it.
+            value = getattr(self.task, '__func__', self.task)
         return super()._repr_item(key, default=default, value=value)
 
 
@@ -706,13 +733,16 @@ class SetAttribute(TaskBase):
     (also for ``read_device``), so the wrapper is free in a device chain.
     """
 
-    def __init__(self, ih, *, start_time=None, sample_rate=None,
-                 **kwargs):
+    def __init__(self, ih, *, start_time=None, sample_rate=None, **kwargs):
         super().__init__(ih, start_time=start_time, sample_rate=sample_rate,
                          **kwargs)
-        if start_time is None and sample_rate is None:
+        keeps_timing = start_time is None and sample_rate is None
+        if keeps_timing:
             self._grid_shift = 0
-        if not set(kwargs).difference(META_ATTRIBUTES):
+        only_labels = set(kwargs) <= META_ATTRIBUTES
+        if only_labels:
+            # Nothing about the samples changes: reads go straight to the
+            # input (also on the device), without a frame in between.
             self.read = self.simple_read
             self.read_device = self.simple_read_device
 

@@ -84,20 +84,30 @@ class FFTBase:
                 f"dtype={self.frequency_dtype}>")
 
 
-class FFTMakerMeta(type):
-    """Registry of FFT maker classes (fourier/base.py:221-253)."""
-    _registry = FFT_MAKER_CLASSES
+def _registry_key(class_name):
+    """``'CudaFFTMaker'`` -> ``'cuda'``: the name a maker is selected by."""
+    key, suffix = class_name.lower(), 'fftmaker'
+    if key.endswith(suffix) and key != suffix:
+        key = key[:-len(suffix)]
+    return key
 
-    def __init__(cls, name, bases, dct):
-        if name != 'FFTMakerBase':
-            key = name.lower()
-            if key.endswith('fftmaker') and len(key) > 8:
-                key = key[:-8]
-            if key in FFTMakerMeta._registry:
-                raise ValueError("key {0} already registered in "
-                                 "FFT_MAKER_CLASSES.".format(key))
-            FFTMakerMeta._registry[key] = cls
-        super().__init__(name, bases, dct)
+
+class FFTMakerMeta(type):
+    """Metaclass that enters every FFT maker class in `FFT_MAKER_CLASSES`.
+
+    Defining ``class FooFFTMaker(FFTMakerBase)`` is all it takes to make
+    ``fft_maker.set('foo')`` work (the plugin seam of the reference,
+    fourier/base.py:221-253); a second class for the same key is an error.
+    """
+
+    def __new__(mcls, name, bases, namespace, **kwargs):
+        cls = super().__new__(mcls, name, bases, namespace, **kwargs)
+        if bases:                   # the root of the hierarchy stays out
+            key = _registry_key(name)
+            if FFT_MAKER_CLASSES.setdefault(key, cls) is not cls:
+                raise ValueError(f"key {key} already registered in "
+                                 "FFT_MAKER_CLASSES.")
+        return cls
 
 
 class FFTMakerBase(metaclass=FFTMakerMeta):
@@ -138,70 +148,73 @@ class FFTMakerBase(metaclass=FFTMakerMeta):
         return f'{type(self).__name__}({settings})'
 
 
-class _StateContext:
-    def __init__(self, parent, value):
-        self._parent = parent
-        self._value = value
+class _Restore:
+    """What `fft_maker.set` returns: leaving the ``with`` block (if it is
+    used as one) puts the previous selection back."""
+
+    def __init__(self, selection, previous):
+        self._selection, self._previous = selection, previous
 
     def __enter__(self):
-        pass
+        return self._selection.get()
 
-    def __exit__(self, type, value, tb):
-        self._parent._value = self._value
+    def __exit__(self, *exc):
+        self._selection._value = self._previous
+        return False
 
     def __repr__(self):
-        return f"<ScienceState {self._parent.__name__}: " \
-               f"{self._parent._value!r}>"
+        return f"<ScienceState fft_maker: {self._selection._value!r}>"
 
 
-class _FFTMakerState(type):
-    @property
-    def system_default(cls):
-        """System default FFT factory."""
-        return cls._system_default
-
-
-class fft_maker(metaclass=_FFTMakerState):
+class _DefaultFFTMaker:
     """Create an FFT with the default maker, or select that default.
 
     ``fft_maker(shape, dtype, direction=..., axis=..., ortho=...,
     sample_rate=...)`` builds a transform with the current default maker;
     ``fft_maker.set('cuda')`` (optionally ``with``) changes the default that
     new tasks capture at construction; ``fft_maker.set(None)`` restores the
-    system default; ``fft_maker.get()`` returns it.
+    system default; ``fft_maker.get()`` returns it.  (The reference keeps this
+    state in an astropy ``ScienceState``, fourier/base.py:348-466; astropy
+    is optional here, so the few operations used are provided directly.)
     """
-    _system_default = None
-    _value = None
+    __name__ = 'fft_maker'
 
-    def __new__(cls, shape, dtype, *,
-                direction='forward', axis=0, ortho=False, sample_rate=None):
-        fft_engine = cls.get()
-        return fft_engine(shape, dtype, direction=direction, axis=axis,
+    def __init__(self):
+        self._system_default = None
+        self._value = None
+
+    @property
+    def system_default(self):
+        """System default FFT factory."""
+        return self._system_default
+
+    def __call__(self, shape, dtype, *, direction='forward', axis=0,
+                 ortho=False, sample_rate=None):
+        return self.get()(shape, dtype, direction=direction, axis=axis,
                           ortho=ortho, sample_rate=sample_rate)
 
-    @classmethod
-    def get(cls):
-        return cls.validate(cls._value)
-
-    @classmethod
-    def validate(cls, value):
-        if value is None:
-            value = cls._system_default
-        if not isinstance(value, FFTMakerBase):
+    def validate(self, value):
+        """The maker ``value`` stands for: itself, or the system default."""
+        maker = self._system_default if value is None else value
+        if not isinstance(maker, FFTMakerBase):
             raise TypeError("Can only set the default to an instance of "
                             "a FFT maker such as CudaFFTMaker().")
-        return value
+        return maker
 
-    @classmethod
-    def set(cls, fft_engine, **kwargs):
-        """Set the FFT factory to be used in new tasks."""
-        if fft_engine is None:
-            fft_engine = cls._system_default
-        elif not isinstance(fft_engine, FFTMakerBase):
+    def get(self):
+        return self.validate(self._value)
+
+    def set(self, fft_engine, **kwargs):
+        """Set the FFT factory to be used in new tasks: a maker instance, the
+        registered name of one (with keyword arguments for it) or None."""
+        if isinstance(fft_engine, str):
             fft_engine = FFT_MAKER_CLASSES[fft_engine](**kwargs)
         elif kwargs:
             raise TypeError("cannot pass keyword arguments except if "
                             "fft_engine is the name of an FFT maker.")
-        ctx = _StateContext(cls, cls._value)
-        cls._value = cls.validate(fft_engine)
-        return ctx
+        restore = _Restore(self, self._value)
+        self._value = self.validate(fft_engine)
+        return restore
+
+
+fft_maker = _DefaultFFTMaker()

@@ -21,69 +21,96 @@ __all__ = ['StreamGenerator', 'EmptyStreamGenerator',
            'payload_levels', 'encode_payload']
 
 
-class StreamGenerator(Base):
+class _FrameSource(Base):
+    """A stream whose frames are made on demand: subclasses say how in
+    ``_make_frame``, which may rely on the sample pointer being at the first
+    sample of the frame asked for."""
+
+    def _make_frame(self):
+        raise NotImplementedError
+
+    def _read_frame(self, frame_index):
+        return self._make_frame()
+
+
+class StreamGenerator(_FrameSource):
     """Generator of data produced by a user-provided function.
 
-    ``function(stream)`` returns ``samples_per_frame`` samples of sample
-    shape ``shape[1:]``; it can count on ``stream.tell()`` being at the start
-    of the frame.
+    Parameters are as for the reference (generators.py:16-90): ``function``
+    is called with the stream itself and returns one frame --
+    ``samples_per_frame`` samples of sample shape ``shape[1:]`` -- for the
+    position ``stream.tell()`` is at; then the shape of the whole stream, its
+    start time, sample rate, frame length and dtype, and optionally
+    ``frequency``, ``sideband`` and ``polarization``.
     """
 
     def __init__(self, function, shape, start_time, sample_rate,
                  samples_per_frame=1, dtype=np.complex64, **kwargs):
+        self._function = function
         super().__init__(shape=shape, start_time=start_time,
                          sample_rate=sample_rate,
                          samples_per_frame=samples_per_frame, dtype=dtype,
                          **kwargs)
-        self._function = function
 
-    def _read_frame(self, frame_index):
+    def _make_frame(self):
         return self._function(self)
 
 
-class EmptyStreamGenerator(Base):
-    """Generator of an empty data stream, to be filled by a `Task`."""
+class EmptyStreamGenerator(_FrameSource):
+    """Generator of a stream of uninitialised frames, to be filled by a
+    `Task` (generators.py:93-151); arguments as for `Base`."""
 
-    def _read_frame(self, frame_index):
-        return np.empty((self.samples_per_frame,) + self.shape[1:],
-                        self.dtype)
+    def _make_frame(self):
+        return np.empty((self.samples_per_frame,) + self.sample_shape,
+                        dtype=self.dtype)
 
 
 class Noise:
-    """Source callable providing reproducible normally distributed frames."""
+    """Callable giving reproducible, normally distributed frames.
+
+    Every frame is drawn from a Philox generator keyed by ``seed`` whose
+    counter is set from the position of the frame in the stream, so a frame
+    is the same whenever and in whatever order it is read, and the stream can
+    be sought (generators.py:154-190).  The draw itself is what makes streams
+    bit-identical to the reference's: ``normal`` in float64 over the frame,
+    the last axis doubled and viewed as complex128 for complex streams, then
+    cast to the stream's dtype.
+    """
 
     def __init__(self, seed=None):
         self.seed = seed
-        self.rng = np.random.Generator(np.random.Philox(self.seed))
-        self.bg_state = self.rng.bit_generator.state
+        self._philox = np.random.Philox(seed)
+        self._fresh = self._philox.state      # counter zero, nothing buffered
+        self._rng = np.random.Generator(self._philox)
 
     def __call__(self, sh):
-        self.bg_state['state']['counter'][1] = sh.tell()
-        self.rng.bit_generator.state = self.bg_state
-        shape = (sh.samples_per_frame,) + sh.sample_shape
+        state = dict(self._fresh)
+        counter = self._fresh['state']['counter'].copy()
+        counter[1] = sh.tell()
+        state['state'] = dict(self._fresh['state'], counter=counter)
+        self._philox.state = state
+        shape = (sh.samples_per_frame,) + tuple(sh.sample_shape)
         if sh.complex_data:
-            shape = shape[:-1] + (shape[-1] * 2,)
-        numbers = self.rng.normal(size=shape)
+            shape = shape[:-1] + (2 * shape[-1],)
+        draws = self._rng.normal(size=shape)
         if sh.complex_data:
-            numbers = numbers.view(np.complex128)
-        return numbers.astype(sh.dtype, copy=False)
+            draws = draws.view(np.complex128)
+        return draws.astype(sh.dtype, copy=False)
 
 
 class NoiseGenerator(StreamGenerator):
     """Generator of a stream of normally distributed noise.
 
-    Data are identical if read multiple times, since the random number
-    generator is re-keyed by the frame offset; choose ``samples_per_frame``
-    large (of order millions of samples).
+    Arguments as for `StreamGenerator` without the function, plus ``seed``.
+    Frames are reproducible (see `Noise`); ``samples_per_frame`` should be
+    large (millions of samples) to keep the cost of re-keying negligible.
     """
 
     def __init__(self, shape, start_time, sample_rate, samples_per_frame,
                  dtype=np.complex64, seed=None, **kwargs):
-        generator = Noise(seed)
-        super().__init__(function=generator, shape=shape,
-                         start_time=start_time, sample_rate=sample_rate,
-                         samples_per_frame=samples_per_frame,
-                         dtype=dtype, **kwargs)
+        super().__init__(Noise(seed), shape, start_time, sample_rate,
+                         samples_per_frame=samples_per_frame, dtype=dtype,
+                         **kwargs)
 
 
 class ArrayStream(Base):

@@ -114,61 +114,56 @@ class Integrate(BaseTaskBase):
 
     def __init__(self, ih, step=None, phase=None, *,
                  start=0, average=True, samples_per_frame=1, dtype=None):
-        self._start = start
-        self._step = step
-
-        ih_start = ih.seek(start)
-        ih_n_sample = ih.shape[0] - ih_start
-        if ih_start < 0 or ih_n_sample < 0:
+        self._start, self._step = start, step
+        # Where in ``ih`` the integration starts: a whole sample the pointer
+        # can be put at, plus -- when ``start`` is a time between samples --
+        # the fraction the bin edges are to be counted from.
+        first = ih.seek(start)
+        n_in = ih.shape[0] - first
+        if first < 0 or n_in < 0:
             raise ValueError("'start' is not within the underlying stream.")
-
-        if not is_index(start):
-            # A time: we may not be at an integer sample.
-            ih_start += to_float((start - ih.time) * ih.sample_rate)
+        if is_index(start):
+            edge0, t_start = first, ih.time
         else:
-            start = ih.time
-
+            edge0 = first + to_float((start - ih.time) * ih.sample_rate)
+            t_start = start
+        # The output grid: how many samples, at what rate, starting where.
         if step is None:
-            step = ih_n_sample
-
+            step = n_in
         if is_index(step):
             assert phase is None, 'cannot pass in phase and integer step'
-            sample_rate = ih.sample_rate / step
-            n_sample = ih_n_sample / step
+            rate_out, n_out = ih.sample_rate / step, n_in / step
+            origin = t_start
         else:
-            stop = ih.stop_time
-            if phase is not None:
-                start = phase(start)
-                stop = phase(stop)
-            sample_rate = 1 / step
-            n_sample = to_float((stop - start) * sample_rate)
-
-        self._mean_offset_size = n_sample / ih_n_sample
-        self._sample_start = start
-
-        n_sample = int(n_sample + 0.5 * self._mean_offset_size)
-        assert n_sample >= 1, "time per frame larger than total time in stream"
-        shape = (n_sample,) + tuple(ih.sample_shape)
-        # Without a phase the start is a time and the rate a frequency --
-        # unless the input itself counts in cycles (a phase-stepped Integrate
-        # or a PulseStack), in which case times come from it (the reference
-        # tells the two apart by the unit of the rate, integration.py:146-151).
-        in_cycles = phase is not None or getattr(ih, '_time_from_ih', False)
-        start_time = False if in_cycles else start
-        self._time_from_ih = in_cycles
-
+            # A time interval, or with ``phase`` an interval in phase.
+            at = (lambda t: t) if phase is None else phase
+            origin, end = at(t_start), at(ih.stop_time)
+            rate_out = 1 / step
+            n_out = to_float((end - origin) * rate_out)
+        # Output samples per input sample (not necessarily 1 / integer), and
+        # the number of output samples: a last one counts if at least half
+        # of it is there.
+        self._mean_offset_size = n_out / n_in
+        self._sample_start = origin
+        n_out = int(n_out + self._mean_offset_size / 2)
+        assert n_out >= 1, "time per frame larger than total time in stream"
+        # Streams that count in cycles (``phase`` given, or the input already
+        # does: a phase-stepped Integrate, a PulseStack) have no start time
+        # of their own; times come from the input (the reference tells the
+        # two apart by the unit of the rate, integration.py:146-151).
+        self._time_from_ih = (phase is not None
+                              or getattr(ih, '_time_from_ih', False))
         if dtype is None:
-            if average:
-                dtype = ih.dtype
-            else:
-                dtype = np.dtype([('data', ih.dtype), ('count', int)])
-
-        super().__init__(ih, shape=shape, sample_rate=sample_rate,
+            dtype = ih.dtype if average else np.dtype(
+                [('data', ih.dtype), ('count', int)])
+        super().__init__(ih, shape=(n_out,) + tuple(ih.sample_shape),
+                         sample_rate=rate_out,
                          samples_per_frame=samples_per_frame,
-                         start_time=start_time, dtype=dtype)
+                         start_time=False if self._time_from_ih else origin,
+                         dtype=dtype)
         self.average = average
         self._phase = phase
-        self._ih_start = ih_start
+        self._ih_start = edge0
         self._setup_source()
 
     # ------------------------------------------------------------- sources
@@ -197,40 +192,55 @@ class Integrate(BaseTaskBase):
         return self.ih._tell_time(self._get_offsets(offset))
 
     def _get_offsets(self, samples, precision=1.e-3, max_iter=10):
-        """Offsets in the underlying stream nearest to the given output
-        sample edges (integration.py:174-228)."""
+        """Sample numbers of ``ih`` at which the output samples ``samples``
+        begin (bin edges; fractional input allowed), as integers.
+
+        Without a phase the edges are evenly spaced:
+        ``around(samples / mean_offset_size + start)`` -- this expression is
+        the contract for bit-exact counts (integration.py:184-186).  With a
+        phase, the sample at which the phase reaches each edge is found by
+        inverting ``phase(t)`` numerically, to ``precision`` samples.
+        """
         if self._phase is None:
             return (np.around(np.asanyarray(samples) / self._mean_offset_size
                               + self._ih_start).astype(int))
+        ih = self.ih
+        shape = np.shape(samples)
+        # Phase, from the start of the integration, each edge should have.
+        want = np.asarray(to_float(np.ravel(samples) / self.sample_rate),
+                          dtype=float)
+        per_sample = float(to_float(self._mean_offset_size
+                                    / self.sample_rate))  # mean phase step
+        n_rel = ih.shape[0] - self._ih_start
 
-        # Requested phases relative to the start.
-        phase = to_float(np.ravel(samples) / self.sample_rate)
-        ih_mean_phase_size = to_float(self._mean_offset_size
-                                      / self.sample_rate)
-        offsets = phase / ih_mean_phase_size
-        all_offsets = np.hstack((0, offsets,
-                                 self.ih.shape[0] - self._ih_start))
-        all_ih_phase = all_offsets * ih_mean_phase_size
-        all_offsets += self._ih_start
-        offsets = all_offsets[1:-1]
-        ih_phase = all_ih_phase[1:-1]
-        mask = np.ones(offsets.shape, bool)
-        it = 0
-        while np.any(mask) and it < max_iter:
-            old_offsets = offsets[mask]
-            ih_time = self.ih.start_time + old_offsets / self.ih.sample_rate
-            ih_phase[mask] = np.asarray(to_float(
-                self._phase(ih_time) - self._sample_start), dtype=float)
-            offsets[mask] = np.interp(phase[mask], all_ih_phase, all_offsets)
-            mask[mask] = abs(offsets[mask] - old_offsets) > precision
-            it += 1
+        def phase_at(rel):
+            t = ih.start_time + (rel + self._ih_start) / ih.sample_rate
+            return np.asarray(to_float(self._phase(t) - self._sample_start),
+                              dtype=float)
 
-        if it >= max_iter:  # pragma: no cover
+        # A secant search per edge, all edges at once: start from where the
+        # mean phase step puts the edge, then follow the local slope.
+        rel = np.clip(want / per_sample, 0., n_rel)
+        got = phase_at(rel)
+        slope = np.full(rel.shape, per_sample)
+        todo = np.ones(rel.shape, bool)
+        for _ in range(max_iter):
+            step = (want[todo] - got[todo]) / slope[todo]
+            new = np.clip(rel[todo] + step, 0., n_rel)
+            new_got = phase_at(new)
+            moved = new - rel[todo]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                local = (new_got - got[todo]) / moved
+            usable = np.isfinite(local) & (local > 0)
+            slope[todo] = np.where(usable, local, slope[todo])
+            rel[todo], got[todo] = new, new_got
+            todo[todo] = np.abs(moved) > precision
+            if not todo.any():
+                break
+        else:  # pragma: no cover
             warnings.warn('offset calculation did not converge. '
                           'This should not happen!')
-
-        shape = getattr(samples, 'shape', ())
-        return offsets.round().astype(int).reshape(shape)
+        return ((rel + self._ih_start).round().astype(int).reshape(shape))
 
     # -------------------------------------------------------------- reading
     def _read_frame(self, frame_index):
@@ -566,34 +576,32 @@ def _cycles(phases):
 class PulseStack(BaseTaskBase):
     """Create a stream of pulse profiles (integration.py:398-477).
 
-    Integrates in ``n_phase`` phase bins per pulse period (an `Integrate` in
-    steps of ``1 / n_phase`` cycles of the ``phase`` callable, which has to
-    include the cycle count) and presents the result as one profile per pulse.
+    One output sample is one pulse: ``n_phase`` bins in phase, each the
+    integral of the input over 1 / n_phase of a cycle of ``phase`` (which has
+    to include the cycle count).  Underneath is an `Integrate` in steps of
+    ``1 / n_phase`` cycles; this class only groups its samples by pulse.
 
     Parameters are as for `Fold`, without ``step``.
     """
 
     def __init__(self, ih, n_phase, phase, *,
                  start=0, average=True, samples_per_frame=1, dtype=None):
-        phased = Integrate(ih, 1. / n_phase, phase, start=start,
-                           average=average,
-                           samples_per_frame=samples_per_frame * n_phase,
-                           dtype=dtype)
-        shape = (phased.shape[0] // n_phase, n_phase) + phased.shape[1:]
-        super().__init__(phased, shape=shape,
-                         sample_rate=phased.sample_rate / n_phase,
-                         samples_per_frame=samples_per_frame,
-                         dtype=dtype)
         self.n_phase = n_phase
+        bins = Integrate(ih, 1. / n_phase, phase, start=start,
+                         average=average, dtype=dtype,
+                         samples_per_frame=samples_per_frame * n_phase)
+        n_pulse = bins.shape[0] // n_phase      # whole pulses only
+        super().__init__(bins, shape=(n_pulse, n_phase) + bins.shape[1:],
+                         sample_rate=bins.sample_rate / n_phase,
+                         samples_per_frame=samples_per_frame, dtype=dtype)
         self._time_from_ih = True    # one sample per cycle, not per second
 
     def _read_frame(self, frame_index):
-        # Read the frame of the phase-binned stream directly.
-        out = self.ih._read_frame(frame_index)
-        if len(out) != self.ih.samples_per_frame:
-            # Remove a possible incomplete cycle in the last frame.
-            out = out[:(len(out) // self.n_phase) * self.n_phase]
-        return out.reshape((-1,) + self.sample_shape)
+        # A frame here is the same frame of the binned stream, cut into
+        # pulses; a last, shorter frame may end with part of a pulse.
+        bins = self.ih._read_frame(frame_index)
+        whole = len(bins) - len(bins) % self.n_phase
+        return bins[:whole].reshape((-1,) + self.sample_shape)
 
     def _tell_time(self, offset):
         return self.ih._tell_time(offset * self.n_phase)
