@@ -85,6 +85,11 @@ def getattr_if_none(ih, attr, value=None, *, required=True, **kwargs):
     return None
 
 
+def _described(name, doc):
+    """Read-only property for the private attribute ``name``."""
+    return property(operator.attrgetter(name), doc=doc)
+
+
 def _same(a, b):
     """Whether two argument values are equal, whatever they are."""
     try:
@@ -202,61 +207,33 @@ class Base:
         broadcast = check_broadcast_to(value, self.sample_shape)
         return simplify_shape(broadcast)
 
-    @property
-    def shape(self):
-        """Shape of the output."""
-        return self._shape
-
-    @property
-    def sample_shape(self):
-        """Shape of a complete sample."""
-        return self.shape[1:]
-
-    @property
-    def samples_per_frame(self):
-        """Number of samples per frame of data."""
-        return self._samples_per_frame
+    # What a stream is described by; all read-only.
+    shape = _described('_shape', "Shape of the output, time axis first.")
+    samples_per_frame = _described(
+        '_samples_per_frame', "Number of samples per frame of data.")
+    dtype = _described('_dtype', "numpy dtype of the samples `read` returns.")
+    sample_rate = _described(
+        '_sample_rate', "Complete samples per second (or per cycle, for "
+        "phase-based streams).")
+    sample_shape = property(lambda self: self.shape[1:],
+                            doc="Shape of a complete sample.")
+    ndim = property(lambda self: len(self.shape),
+                    doc="Number of axes of the stream seen as an array.")
+    complex_data = property(lambda self: self._dtype.kind == 'c',
+                            doc="Whether the samples are complex.")
+    # Times follow from offsets through `_tell_time`, which tasks with
+    # unevenly spaced samples override.
+    start_time = property(lambda self: self._tell_time(0),
+                          doc="Start time of the output.")
+    time = property(lambda self: self._tell_time(self.offset),
+                    doc="Time of the sample pointer's current offset.")
+    stop_time = property(lambda self: self._tell_time(self.shape[0]),
+                         doc="Time just after the last sample.")
 
     @property
     def size(self):
         """Total number of values: samples times values per sample."""
         return int(np.prod(self.shape, dtype=object)) if self.shape else 1
-
-    @property
-    def ndim(self):
-        """Number of axes of the stream seen as an array (time first)."""
-        return len(self.shape)
-
-    @property
-    def dtype(self):
-        """numpy dtype of the samples that `read` returns."""
-        return self._dtype
-
-    @property
-    def complex_data(self):
-        """Whether the samples are complex."""
-        return self._dtype.kind == 'c'
-
-    @property
-    def sample_rate(self):
-        """Complete samples per second (or per cycle, for phase-based
-        streams)."""
-        return self._sample_rate
-
-    @property
-    def start_time(self):
-        """Start time of the output."""
-        return self._tell_time(0)
-
-    @property
-    def time(self):
-        """Time of the sample pointer's current offset in the output."""
-        return self._tell_time(self.offset)
-
-    @property
-    def stop_time(self):
-        """Time at the end of the output, just after the last sample."""
-        return self._tell_time(self.shape[0])
 
     # --------------------------------------------------------- positioning
     def seek(self, offset, whence=0):
