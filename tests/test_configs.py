@@ -212,3 +212,59 @@ def test_empty_and_edge_reads(bt):
     assert pw.read().shape == (1, 64, 4)
     with pytest.raises(AssertionError):
         bt.Channelize(dd, 1 << 15)     # frame larger than the stream
+
+
+@pytest.mark.parametrize('which', ['C4', 'C2'])
+def test_bench_block_shape(bt, which):
+    """The block shape bench.py launches (many frames in ONE launch of every
+    kernel): 8 frames of 2^24 x 2 series (C4), 16 frames of 2^20 x 16 series
+    (C2).  The first, a middle and the last frame of the dedispersed block
+    against the oracle, and the integrated spectra of those frames."""
+    if which == 'C4':
+        rate, freq, dm, N, n_frames = 512e6, 8192e6, 1000., 1 << 24, 8
+        shape, pads = (2,), (1889551, 2075345)
+    else:
+        rate, dm, N, n_frames = 8e6, 100., 1 << 20, 16
+        freq = (1372e6 + 8e6 * np.arange(8)).reshape(8, 1)
+        shape, pads = (8, 2), (74847, 80161)
+    spf = N - sum(pads)
+    n = (n_frames - 1) * spf + N
+    g = np.random.default_rng(4242)
+    # float32 draws directly: the block is 1.7 GB (C4).
+    x = np.empty((n,) + shape, np.complex64)
+    xv = x.view(np.float32)
+    step = 1 << 22
+    for i in range(0, n, step):
+        xv[i:i + step] = g.standard_normal(xv[i:i + step].shape,
+                                           dtype=np.float32)
+    src = bt.ArrayStream(bt._buffers.as_device(x), t0(bt), rate,
+                         samples_per_frame=1 << 20, frequency=freq,
+                         sideband=1, polarization=np.array(['X', 'Y']))
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    assert (dd._pad_start, dd._pad_end) == pads
+    assert dd._ih_samples_per_frame == N and dd.shape[0] == n_frames * spf
+    dd.read_device(1)                    # creates the plan (chirp kernel)
+    dd.seek(0)
+    launches0 = bt._cabi.lib().bbt_launch_count()
+    y = dd.read_device()                 # all frames, one launch per pass
+    assert bt._cabi.lib().bbt_launch_count() - launches0 == 3
+    it = bt.Integrate(bt.Power(bt.Channelize(dd, 1024)), 8, average=False)
+    spectra = it.read()
+    for f in (0, n_frames // 2, n_frames - 1):
+        xf = x[f * spf:f * spf + N]
+        op = orc.DispersePlan(-dm, np.asarray(freq) / 1e6, 1, rate / 1e6, True,
+                              N, N, shape, samples_per_frame=spf,
+                              fast_len=orc.next_pow2)
+        want = orc.disperse(xf, op)
+        assert want.shape[0] == spf
+        got = y[f * spf:(f + 1) * spf].cpu().numpy()
+        assert_voltage(got, want)
+        # Integration bins of 8 spectra that lie wholly inside this frame.
+        b0 = -(-f * spf // (8 * 1024))
+        b1 = (f + 1) * spf // (8 * 1024)
+        lo = b0 * 8 * 1024 - f * spf
+        power = orc.power(orc.channelize(want[lo:lo + (b1 - b0) * 8192],
+                                         1024), axis=-1)
+        wsum = power.reshape((b1 - b0, 8) + power.shape[1:]).sum(1)
+        assert np.all(spectra['count'][b0:b1] == 8)
+        assert_power(spectra['data'][b0:b1], wsum)
