@@ -18,6 +18,11 @@ struct bbt_dedisperse_plan {
   cf* big_hi;
   cf* chirp;        // [n_chirp][n1][n2]
   int* series_map;  // device
+  // Chirp parameters kept on the device for the regenerating row pass.
+  double* d_freq;
+  double* d_fref;
+  signed char* d_sb;
+  double ch_d, ch_rate, ch_soff;
 };
 
 namespace {
@@ -163,7 +168,8 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
       if (reinterpret_cast<uintptr_t>(a.work) & 15)
         return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
       const size_t smem = Row2Cfg<C>::kSmemBytes;
-      auto kern = dd_row2_kernel<C>;
+      const bool regen = a.ch_freq && tune("chirp_regen", 0);
+      auto kern = regen ? dd_row2_kernel<C, true> : dd_row2_kernel<C, false>;
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
       const int64_t ctas =
@@ -256,6 +262,9 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->log2n = l;
   p->big_lo = p->big_hi = p->chirp = nullptr;
   p->series_map = nullptr;
+  p->d_freq = p->d_fref = nullptr;
+  p->d_sb = nullptr;
+  p->ch_d = p->ch_rate = p->ch_soff = 0.;
   p->planar = 1;
   if (!hint) hint = tune("dd_hint", 0);
   p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
@@ -357,9 +366,10 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     if (!rc && cudaStreamSynchronize(0) != cudaSuccess)
       rc = fail(BBT_ECUDA, "chirp kernel failed");
 #endif
-    dev_free(dfreq);
-    dev_free(dref);
-    dev_free(dsb);
+    p->d_freq = static_cast<double*>(dfreq);
+    p->d_fref = static_cast<double*>(dref);
+    p->d_sb = static_cast<signed char*>(dsb);
+    p->ch_d = ca.d, p->ch_rate = rate_mhz, p->ch_soff = sample_offset;
     if (rc) {
       bbt_dedisperse_plan_destroy(p);
       return rc;
@@ -372,6 +382,9 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
 int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* p,
                                      const void* host_response) {
   if (!p || !host_response) return fail(BBT_EINVAL, "null argument");
+  // An arbitrary response cannot be regenerated from chirp parameters.
+  if (p->d_freq) dev_free(p->d_freq);
+  p->d_freq = nullptr;
   const int64_t total = p->n_chirp * p->n;
   void* tmp = nullptr;
   if (dev_alloc(&tmp, total * sizeof(cf)))
@@ -472,6 +485,8 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.tw = p->tw2;
   a.tw1 = p->tw1;
   a.tw_sub = p->tw_sub;
+  a.ch_freq = p->d_freq, a.ch_fref = p->d_fref, a.ch_sb = p->d_sb;
+  a.ch_d = p->ch_d, a.ch_rate = p->ch_rate, a.ch_soff = p->ch_soff;
   a.big = BigTwiddle{p->big_lo, p->big_hi};
   a.chirp = p->chirp;
   a.series_map = p->series_map;
@@ -534,6 +549,9 @@ int bbt_dedisperse_plan_destroy(bbt_dedisperse_plan* p) {
   if (p->big_hi) dev_free(p->big_hi);
   if (p->chirp) dev_free(p->chirp);
   if (p->series_map) dev_free(p->series_map);
+  if (p->d_freq) dev_free(p->d_freq);
+  if (p->d_fref) dev_free(p->d_fref);
+  if (p->d_sb) dev_free(p->d_sb);
   delete p;
   return BBT_OK;
 }

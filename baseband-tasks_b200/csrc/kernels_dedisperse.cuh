@@ -32,6 +32,12 @@ struct DdArgs {
   const cf* tw;         // N2-th roots of unity (row FFTs, single-pass frames)
   const cf* tw1;        // N1-th roots of unity (column FFTs)
   const cf* tw_sub;     // (N2/32)-th roots of unity (dd_row2_kernel)
+  // Chirp parameters, for regenerating the chirp in the row pass instead of
+  // reading the cached table (A/B variant, tuning knob chirp_regen).
+  const double* ch_freq;
+  const double* ch_fref;
+  const signed char* ch_sb;
+  double ch_d, ch_rate, ch_soff;
   BigTwiddle big;       // W_N^m
   const cf* chirp;      // [n_chirp][N1][N2]
   const int* series_map;  // series -> chirp index
@@ -515,6 +521,27 @@ BBT_HD long long row2_bin(long long pos, int log2n2) {  // inverse of row2_pos
   return (rem / Ts) + 32 * ((rem % Ts) + Ts * e);
 }
 
+// One chirp value from float64 phase (the arithmetic of chirp_kernel with the
+// final sincos in float32 of the phase reduced to [-1/2, 1/2] cycles).
+BBT_DEV cf chirp_value(double freq, double fref, double sb, double d,
+                       double rate_mhz, double soff, long long k, long long N) {
+  const long long ks = (k < (N + 1) / 2) ? k : k - N;
+  const double fftfreq = (double)ks * (rate_mhz / (double)N);
+  const double f = freq + fftfreq * sb;
+  const double u = 1. / fref - 1. / f;
+  double phase = d * f * (u * u) * 1e6 * sb;
+  if (soff != 0.) phase += soff / rate_mhz * fftfreq;
+  phase -= rint(phase);
+  float sn, cs;
+#if defined(__CUDA_ARCH__)
+  sincospif(2.f * (float)phase, &sn, &cs);
+#else
+  sn = sinf(6.283185307179586f * (float)phase);
+  cs = cosf(6.283185307179586f * (float)phase);
+#endif
+  return mk(cs, sn);
+}
+
 template <class C>
 struct Row2Cfg {
   static constexpr int M = C::T;                    // points per sub-transform
@@ -532,11 +559,17 @@ struct Row2Cfg {
       (kTabOuter + CS::twtab_size()) * sizeof(cf);
 };
 
-template <class C>
+struct ChirpRegen {          // per row: what chirp_value needs
+  double freq, fref, sb, d, rate_mhz, soff;
+  long long k1, n1, N;
+  int log2n2;
+};
+
+template <class C, bool REGEN>
 BBT_DEV_NOINLINE void dd_row2_tile(
     cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw,
     const cf* tw_sub, bool valid, unsigned phase, const char* next_src,
-    unsigned next_bytes) {
+    unsigned next_bytes, const ChirpRegen* rg) {
   static_assert(C::LOG2E == 5 && C::LOG2N >= 10, "32 values per thread");
   using R = Row2Cfg<C>;
   using CS = typename R::CS;
@@ -572,9 +605,21 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   SmemWarp<CS::PADSHIFT> sw{mine, tab_sub};
   block_fft<CS>(v, tt, tw_sub, sw);
   if (valid) {
+    if constexpr (REGEN) {
+      // The chirp from float64 phase instead of the cached table: bin
+      // k1 + n1 kk of the frame, kk the bin of the row this thread holds.
 #pragma unroll
-    for (int e = 0; e < 32; ++e)
-      v[e] = cconj(cmul(v[e], ldtw(chirp, u + M * e)));
+      for (int e = 0; e < 32; ++e) {
+        const long long kk = row2_bin(u + M * e, rg->log2n2);
+        v[e] = cconj(cmul(v[e], chirp_value(rg->freq, rg->fref, rg->sb, rg->d,
+                                            rg->rate_mhz, rg->soff,
+                                            rg->k1 + rg->n1 * kk, rg->N)));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        v[e] = cconj(cmul(v[e], ldtw(chirp, u + M * e)));
+    }
   }
   block_fft<CS>(v, tt, tw_sub, sw);
   {
@@ -607,7 +652,7 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   }
 }
 
-template <class C>
+template <class C, bool REGEN>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   Mbar* bar = reinterpret_cast<Mbar*>(smem + Row2Cfg<C>::kElems);
@@ -683,8 +728,16 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
           bulk_prefetch_l2(next_src + o,
                            next_bytes - o < kChunk ? next_bytes - o : kChunk);
     }
-    dd_row2_tile<C>(smem, bar, row, chirp, a.tw, a.tw_sub, valid, k, next_src,
-                    next_bytes);
+    ChirpRegen rg;
+    if (REGEN && valid) {
+      const int c = a.series_map[s];
+      rg.freq = a.ch_freq[c], rg.fref = a.ch_fref[c];
+      rg.sb = (double)a.ch_sb[c], rg.d = a.ch_d;
+      rg.rate_mhz = a.ch_rate, rg.soff = a.ch_soff;
+      rg.k1 = k1, rg.n1 = n1, rg.N = a.N, rg.log2n2 = a.log2n2;
+    }
+    dd_row2_tile<C, REGEN>(smem, bar, row, chirp, a.tw, a.tw_sub, valid, k,
+                           next_src, next_bytes, &rg);
   }
 }
 
