@@ -938,6 +938,90 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
   }
 }
 
+// The same for real input (float32 or raw int8) with the FIR done as a
+// separate, vectorised phase: all threads of the CTA walk over the tile's
+// G n values four at a time (one 32-bit load of four 8-bit samples, or one
+// 128-bit load of four floats, per tap -- coalesced, where pfb_kernel issues
+// one byte load per thread, tap and value), and leave the filtered block in
+// shared memory, in the buffer the transform then exchanges through; the
+// transform threads pick their values up from there.  Needs G % inner == 0
+// (a tile is G / inner whole spectra of all columns) and n inner % 4 == 0.
+template <class C, int KIND>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    pfb_real_kernel(PfbArgs a) {
+  static_assert(KIND == 1 || KIND == 2, "real input");
+  cf* smem = BBT_SMEM(cf);
+  float* y = reinterpret_cast<float*>(smem);
+  const int tid = threadIdx.x;
+  const int g = tid % C::G, t = tid / C::G;
+  const int inner = (int)a.inner;
+  const int J = C::G / inner;                       // spectra per tile
+  const long long j0 = (long long)blockIdx.x * J;
+  const int block = C::N * inner;                   // values per spectrum
+  const int ys = block + 16;                        // pitch in y (bank shift)
+  // Phase 1: y[jl][q] = sum_tap h[tap][q / inner] x[(j0 + jl + tap) n inner + q].
+  for (int w = tid; w < J * block / 4; w += C::THREADS) {
+    const int q4 = w * 4;
+    const int jl = q4 / block, q = q4 - jl * block;
+    if (j0 + jl >= a.n_spec) continue;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // Filter coefficient of each of the four values (same for every tap).
+    int hi[4];
+    if (inner == 2) {
+      hi[0] = hi[1] = q >> 1;
+      hi[2] = hi[3] = (q >> 1) + 1;
+    } else if (inner == 1) {
+      hi[0] = q, hi[1] = q + 1, hi[2] = q + 2, hi[3] = q + 3;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) hi[r] = (q + r) / inner;
+    }
+    for (int tap = 0; tap < a.n_tap; ++tap) {
+      const long long at = (j0 + jl + tap) * (long long)block + q;
+      float x[4];
+      if (KIND == 2) {
+        const unsigned word =
+            *reinterpret_cast<const unsigned*>(
+                static_cast<const signed char*>(a.in) + at);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          x[r] = (float)(signed char)((word >> (8 * r)) & 0xffu);
+      } else {
+        const f4 v = *reinterpret_cast<const f4*>(
+            static_cast<const float*>(a.in) + at);
+        x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+      }
+      const float* h = a.h + (long long)tap * C::N;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        acc[r] = fmaf(BBT_LDGF(h + hi[r]), x[r], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[jl * ys + q + r] = acc[r];
+  }
+  BBT_SYNC();
+  // Phase 2: lanes are (spectrum, column) pairs, column fastest.
+  const int jl = g / inner, c = g - jl * inner;
+  const long long j = j0 + jl;
+  const bool valid = j < a.n_spec;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e)
+    v[e] = mk(valid ? y[jl * ys + (t + C::T * e) * inner + c] : 0.f, 0.f);
+  BBT_SYNC();  // y becomes the exchange buffer
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  block_fft<C>(v, t, a.tw, sm);
+  if (valid) {
+    const long long n_chan = C::N / 2 + 1;
+    cf* dst = a.out + (j * n_chan) * a.inner + c;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      const int k = t + C::T * e;
+      if (k <= C::N / 2) dst[k * a.inner] = v[e];
+    }
+  }
+}
+
 // Integer sample shifts per series (sampling.py:380-425):
 // out[i][s] = in[i + offset[s]][s] for items of 4 or 8 bytes.
 template <typename T>
