@@ -195,14 +195,129 @@ struct BigTwiddle {
   }
 };
 
+// data is [batch][n1][n2][inner].
 BBT_GLOBAL void twiddle_kernel(cf* data, long long n1, long long n2,
-                               long long batch, BigTwiddle tw, int conj) {
-  const long long total = batch * n1 * n2;
+                               long long batch, long long inner, BigTwiddle tw,
+                               int conj) {
+  const long long total = batch * n1 * n2 * inner;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i % (n1 * n2);
+    const long long r = (i / inner) % (n1 * n2);
     cf w = tw.get((r / n2) * (r % n2));
     data[i] = conj ? cmulc(data[i], w) : cmul(data[i], w);
+  }
+}
+
+// [batch][rows][cols][inner] -> [batch][cols][rows][inner] for inner > 1
+// (writes coalesced; runs of `inner` values on the reading side).
+BBT_GLOBAL void transpose_inner_kernel(const cf* BBT_RESTRICT in,
+                                       cf* BBT_RESTRICT out, long long batch,
+                                       long long rows, long long cols,
+                                       long long inner) {
+  const long long total = batch * rows * cols * inner;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long c = o % inner, q = o / inner;
+    const long long r = q % rows, q2 = q / rows;
+    const long long col = q2 % cols, b = q2 / cols;
+    out[o] = in[((b * rows + r) * cols + col) * inner + c];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Helpers of the general FFT plan (bbt_fft.cu): transforms of any length n
+// through power-of-two transforms of length m >= 2n - 1 (Bluestein: with
+// a_j = exp(-i pi j^2 / n), X_k = a_k sum_j (x_j a_j) conj(a)_{k-j}), and real
+// transforms through complex ones.  Data are [outer][len][inner].
+struct AxisArgs {
+  const void* in;
+  void* out;
+  const cf* chirp;     // a_j, j < n (or the filter B_j, j < m)
+  long long outer, inner;
+  long long n_in;      // length of the axis in `in`
+  long long n_out;     // length of the axis in `out`
+  long long n;         // transform length (Hermitian extension)
+  int in_real;         // input is float32 rather than complex64
+  int out_real;        // output is float32
+  int conj_in;         // conjugate the input (inverse transforms)
+  int conj_out;        // conjugate the output
+  float scale;
+};
+
+// out[b][j][c] = (j < n_in ? in[b][j][c] (conjugated?) * chirp[j] : 0) for
+// j < n_out: multiply by the chirp and zero-pad.  With chirp == nullptr the
+// values are only converted / copied (real -> complex, truncation).
+BBT_GLOBAL void axis_pre_kernel(AxisArgs a) {
+  const long long total = a.outer * a.n_out * a.inner;
+  cf* out = static_cast<cf*>(a.out);
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long c = o % a.inner, q = o / a.inner;
+    const long long j = q % a.n_out, b = q / a.n_out;
+    cf x = mk(0.f, 0.f);
+    if (j < a.n_in) {
+      const long long i = (b * a.n_in + j) * a.inner + c;
+      x = a.in_real ? mk(static_cast<const float*>(a.in)[i], 0.f)
+                    : static_cast<const cf*>(a.in)[i];
+      if (a.conj_in) x = cconj(x);
+      if (a.chirp) x = cmul(x, a.chirp[j]);
+    }
+    out[o] = x;
+  }
+}
+
+// Hermitian extension of half spectra [outer][n/2+1][inner] to
+// [outer][n][inner], as numpy's irfft reads them (imaginary parts of bins 0
+// and n/2 ignored); optionally conjugated and times the chirp.
+BBT_GLOBAL void axis_hermitian_kernel(AxisArgs a) {
+  const long long total = a.outer * a.n_out * a.inner;
+  const cf* in = static_cast<const cf*>(a.in);
+  cf* out = static_cast<cf*>(a.out);
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long c = o % a.inner, q = o / a.inner;
+    const long long j = q % a.n_out, b = q / a.n_out;
+    cf x = mk(0.f, 0.f);
+    if (j < a.n) {
+      const long long h = j <= a.n / 2 ? j : a.n - j;
+      x = in[(b * a.n_in + h) * a.inner + c];
+      if (j == 0 || 2 * j == a.n) x.y = 0.f;
+      if (j > a.n / 2) x = cconj(x);
+      if (a.conj_in) x = cconj(x);
+      if (a.chirp) x = cmul(x, a.chirp[j]);
+    }
+    out[o] = x;
+  }
+}
+
+// data[b][j][c] *= filter[j]  (j < n_out).
+BBT_GLOBAL void axis_filter_kernel(AxisArgs a) {
+  const long long total = a.outer * a.n_out * a.inner;
+  cf* data = static_cast<cf*>(a.out);
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long j = (o / a.inner) % a.n_out;
+    data[o] = cmul(data[o], a.chirp[j]);
+  }
+}
+
+// out[b][k][c] = in[b][k][c] * chirp[k] * scale (conjugated?) for k < n_out,
+// taken from an axis of length n_in; as complex64 or its real part.
+BBT_GLOBAL void axis_post_kernel(AxisArgs a) {
+  const long long total = a.outer * a.n_out * a.inner;
+  const cf* in = static_cast<const cf*>(a.in);
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const long long c = o % a.inner, q = o / a.inner;
+    const long long k = q % a.n_out, b = q / a.n_out;
+    cf x = in[(b * a.n_in + k) * a.inner + c];
+    if (a.chirp) x = cmul(x, a.chirp[k]);
+    x = cscale(x, a.scale);
+    if (a.conj_out) x = cconj(x);
+    if (a.out_real)
+      static_cast<float*>(a.out)[o] = x.x;
+    else
+      static_cast<cf*>(a.out)[o] = x;
   }
 }
 

@@ -6,10 +6,14 @@ makers register themselves (fourier/base.py:235-253), and selectable with
 unnormalised forward transform, 1/n on the inverse, 1/sqrt(n) both ways with
 ``ortho`` (fourier/base.py:95-104); real transforms keep n//2+1 bins.
 
-Deliberate limits (no CPU fallback): lengths must be powers of two --
-``next_fast_len`` rounds up so padded tasks choose such lengths themselves
-(dispersion.py:99, base.py:757-758) -- and arithmetic is single precision
-(double-precision input is converted, with a warning).
+Any length and axis is transformed on the GPU: powers of two up to 16384 in
+one kernel, larger ones in four steps, other lengths through Bluestein's
+algorithm on a power-of-two length (about three times the work, so
+``next_fast_len`` rounds up to a power of two and padded tasks choose such
+lengths themselves, dispersion.py:99, base.py:757-758); real transforms beyond
+the single-kernel sizes go through the complex transform.  Arithmetic is
+single precision (double-precision input is converted, with a warning).  There
+is no CPU fallback.
 """
 import ctypes
 import math
@@ -61,16 +65,12 @@ class CudaFFTBase(FFTBase):
                                               self._frequency_dtype)
             self._out_shape, self._out_dtype = (self._time_shape,
                                                 self._time_dtype)
-        # Lengths above the single-pass limit run on a contiguous axis.
-        self._transpose = self._n > 8192 and self._inner > 1
 
     def _get_plan(self):
         if self._plan is None:
             lib = _cabi.lib()
             plan = ctypes.c_void_p()
             outer, inner = self._outer, self._inner
-            if self._transpose:
-                outer, inner = outer * inner, 1
             lib.check(lib.bbt_fft_plan_create(
                 ctypes.byref(plan), self._n, outer, inner, self._kind,
                 _cabi.BBT_BACKWARD if self.direction == 'backward'
@@ -105,24 +105,19 @@ class CudaFFTBase(FFTBase):
         x = B.as_device(a, dtype=single_in)
         lib = _cabi.lib()
         plan = self._get_plan()
-        if self._transpose:
-            axis = self._axis % len(self._in_shape)
-            x = x.movedim(axis, -1).contiguous()
-            out = B.empty(x.shape, single_out)
-        elif (out is not None and out.is_contiguous()
-              and out.dtype == B.torch_dtype(single_out)
-              and out.numel() == int(np.prod(self._out_shape, dtype=np.int64))):
-            lib.check(lib.bbt_fft_exec(
-                plan, B.ptr(x), B.ptr(out), B.ptr(self._get_work()),
-                _cabi.stream_ptr()))
-            return out
-        else:
+        if (out is None or not out.is_contiguous()
+                or out.dtype != B.torch_dtype(single_out)
+                or out.numel() != int(np.prod(self._out_shape,
+                                              dtype=np.int64))):
             out = B.empty(self._out_shape, single_out)
-        work = self._get_work()
-        lib.check(lib.bbt_fft_exec(plan, B.ptr(x), B.ptr(out), B.ptr(work),
+            given = False
+        else:
+            given = True
+        lib.check(lib.bbt_fft_exec(plan, B.ptr(x), B.ptr(out),
+                                   B.ptr(self._get_work()),
                                    _cabi.stream_ptr()))
-        if self._transpose:
-            out = out.movedim(-1, axis).contiguous()
+        if given:
+            return out
         if self._out_dtype != single_out:
             out = out.to(B.torch_dtype(self._out_dtype))
         return B.as_host(out) if host else out
@@ -143,13 +138,9 @@ class CudaFFTMaker(FFTMakerBase):
     def __call__(self, shape, dtype, direction='forward', axis=0, ortho=False,
                  sample_rate=None):
         n = tuple(shape)[axis]
-        if n < 2 or n & (n - 1):
-            raise NotImplementedError(
-                f"the cuda FFT maker needs power-of-two lengths, got {n}; "
-                "use CudaFFTMaker.next_fast_len to choose frame sizes.")
-        if n > 8192 and np.dtype(dtype).kind == 'f':
-            raise NotImplementedError(
-                "real transforms above 8192 points are not implemented.")
+        if n < 2:
+            raise NotImplementedError("the cuda FFT maker needs at least two "
+                                      "points along the transform axis.")
         return super().__call__(shape=shape, dtype=dtype, direction=direction,
                                 axis=axis, ortho=ortho,
                                 sample_rate=sample_rate)

@@ -45,8 +45,11 @@ const char* bbt_last_error(void);
 /* ---- FFT: replaces np.fft.{fft,ifft,rfft,irfft}(a, axis, norm) as called by
  * NumpyFFTBase (fourier/numpy.py:33-49) for the FFT objects FFTMakerBase.__call__
  * creates (fourier/base.py:262-311).  Data are [outer][n][inner]; the
- * transform runs along the middle axis.  n must be a power of two; n > 16384
- * needs inner == 1 and a work buffer of bbt_fft_plan_work_bytes().
+ * transform runs along the middle axis.  Any n >= 2: powers of two up to
+ * 16384 run in one kernel, larger ones in four steps, other lengths through
+ * Bluestein's algorithm on a power-of-two length; real transforms beyond the
+ * single-kernel sizes go through the complex transform.  All but the
+ * single-kernel case need a work buffer of bbt_fft_plan_work_bytes().
  * scale multiplies the output (1, 1/n or 1/sqrt(n): fourier/base.py:95-104). */
 int bbt_fft_plan_create(bbt_fft_plan** plan, int64_t n, int64_t outer,
                         int64_t inner, int kind, int direction, double scale);

@@ -55,8 +55,11 @@ def test_channelize_task(bt, complex_data):
         bt.Channelize(fh, 65536)
     with pytest.raises(AssertionError):
         bt.Channelize(fh, 400001)
-    with pytest.raises(NotImplementedError):  # documented: powers of two only
-        bt.Channelize(fh, 1000)
+    # Any number of channels: 1000 is not a power of two (chirp-z transform).
+    c1000 = bt.Channelize(fh, 1000)
+    ref1000 = (np.fft.fft if complex_data else np.fft.rfft)(
+        x[:40000].reshape(-1, 1000, 8), axis=1)
+    assert_voltage(c1000.read(), ref1000.astype('c8'))
 
 
 @pytest.mark.parametrize('spf', [1, 16, 33])

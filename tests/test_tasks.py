@@ -60,8 +60,12 @@ def test_fft_maker_registry(bt):
             pass
     assert CudaFFTMaker.next_fast_len(130) == 256
     assert CudaFFTMaker.next_fast_len(256) == 256
-    with pytest.raises(NotImplementedError):
-        fft_maker((7919,), 'c8')
+    # Any length is taken (the reference's plugin test runs every maker on a
+    # prime length, fourier/tests/test_fourier.py:49,89).
+    x = cnoise(np.random.default_rng(7919), (7919,))
+    fft = fft_maker((7919,), 'c8')
+    assert_voltage(fft(x), np.fft.fft(x))
+    assert_voltage(fft.inverse()(fft(x)), x)
 
 
 def test_fft_object(bt):
@@ -116,6 +120,18 @@ def test_fft_large_strided(bt):
     x = cnoise(np.random.default_rng(3), (1 << 14, 2))
     fft = fft_maker(x.shape, 'c8', axis=0)
     assert_voltage(fft(x), np.fft.fft(x, axis=0))
+    # Above the single-kernel length along a strided axis, complex and real,
+    # and a frame length of the reference's default (2-3-5-7 smooth) framing.
+    x = cnoise(np.random.default_rng(4), (1 << 15, 2))
+    assert_voltage(fft_maker(x.shape, 'c8', axis=0)(x), np.fft.fft(x, axis=0))
+    r = np.random.default_rng(5).normal(size=(1 << 15, 2)).astype('f4')
+    rfft = fft_maker(r.shape, 'f4', axis=0)
+    R = rfft(r)
+    assert R.shape == ((1 << 14) + 1, 2)
+    assert_voltage(R, np.fft.rfft(r, axis=0).astype('c8'))
+    assert_voltage(rfft.inverse()(R), r)
+    s = cnoise(np.random.default_rng(6), (3, 19324))
+    assert_voltage(fft_maker(s.shape, 'c8', axis=1)(s), np.fft.fft(s, axis=1))
 
 
 # --------------------------------------------------------------------- dm
