@@ -46,6 +46,8 @@ _SIGNATURES = {
     'bbt_dedisperse_plan_destroy': (c_int, [c_void_p]),
     'bbt_power_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int64,
                                c_void_p]),
+    'bbt_multiply_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_void_p]),
     'bbt_square_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int,
                                 c_void_p]),
     'bbt_channelize_power_exec': (c_int, [c_void_p, c_void_p, c_int64,

@@ -17,6 +17,16 @@ int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
   return check_launch("power kernel");
 }
 
+int bbt_multiply_exec(const void* a, const void* b, void* out, int64_t n,
+                      void* stream) {
+  if (!a || !b || !out) return fail(BBT_EINVAL, "null argument");
+  if (n <= 0) return BBT_OK;
+  BBT_LAUNCH(multiply_kernel, dim3(grid_for(n, 256)), dim3(256), 0,
+             as_stream(stream), static_cast<const cf*>(a),
+             static_cast<const cf*>(b), static_cast<cf*>(out), (long long)n);
+  return check_launch("multiply kernel");
+}
+
 int bbt_square_exec(const void* in, void* out, int64_t n, int is_complex,
                     void* stream) {
   if (!in || !out) return fail(BBT_EINVAL, "null argument");

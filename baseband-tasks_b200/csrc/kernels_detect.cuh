@@ -40,6 +40,15 @@ BBT_GLOBAL void power_kernel(const cf* BBT_RESTRICT in, float* BBT_RESTRICT out,
   }
 }
 
+// out[i] = a[i] * b[i], complex64 (the frequency-domain multiply of
+// dispersion.py:137 for frame lengths the fused plan does not take).
+BBT_GLOBAL void multiply_kernel(const cf* BBT_RESTRICT a, const cf* BBT_RESTRICT b,
+                                cf* BBT_RESTRICT out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = cmul(a[i], b[i]);
+}
+
 BBT_GLOBAL void square_kernel(const float* BBT_RESTRICT in, float* BBT_RESTRICT out,
                               long long n, int is_complex) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;

@@ -129,6 +129,12 @@ class Disperse(PaddedTaskBase):
         self._n_series = len(keys)
         self._plan = None
         self._work = None
+        # Frame lengths the fused plan does not take (not a power of two: the
+        # reference's own framing, CudaFFTMaker(fast_len='reference')) go
+        # frame by frame through the FFT plans: fft, x phase factor, ifft.
+        n = self._ih_samples_per_frame
+        self._generic = bool(n & (n - 1))
+        self._generic_parts = None
 
     # ------------------------------------------------------------- the plan
     def _get_plan(self):
@@ -204,6 +210,8 @@ class Disperse(PaddedTaskBase):
         shape ``(N,) + sample_shape``."""
         lib = _cabi.lib()
         n = self._ih_samples_per_frame
+        if self._generic:
+            return self._host_phase_factor()
         if self._real:
             return self._real_phase_factor()[self._series_map].T.reshape(
                 (n // 2 + 1,) + self.ih.sample_shape)
@@ -225,9 +233,11 @@ class Disperse(PaddedTaskBase):
         starts at ``i*samples_per_frame``.  Returns (or fills ``out`` with)
         the ``n_frames*samples_per_frame`` valid output samples.
         """
+        host = not B.is_tensor(data)
+        if self._generic:
+            return self._task_frames_generic(data, n_frames, out, host)
         lib = _cabi.lib()
         plan = self._get_plan()
-        host = not B.is_tensor(data)
         if self._real:
             return self._task_frames_real(data, n_frames, out, host)
         result = self._exec_frames(B.as_device(data, dtype=np.complex64),
@@ -260,6 +270,61 @@ class Disperse(PaddedTaskBase):
             out.copy_(result)
             return out
         return result
+
+    def _task_frames_generic(self, data, n_frames, out, host):
+        """Any frame length: what `Disperse.task` of the reference does
+        (dispersion.py:135-139), with the transforms on the GPU."""
+        lib = _cabi.lib()
+        single = np.float32 if self._real else np.complex64
+        x = B.as_device(data, dtype=single)
+        if self._generic_parts is None:
+            fft = self._fft
+            factor = B.as_device(np.ascontiguousarray(
+                np.broadcast_to(self._host_phase_factor(),
+                                fft.frequency_shape), dtype=np.complex64))
+            self._generic_parts = (fft, fft.inverse(), factor)
+        fft, ifft, factor = self._generic_parts
+        N, spf = self._ih_samples_per_frame, self.samples_per_frame
+        direct = (out is not None and out.is_contiguous()
+                  and out.dtype == B.torch_dtype(single))
+        result = out if direct else B.empty(
+            (n_frames * spf,) + self.sample_shape, single)
+        for f in range(n_frames):
+            ft = fft(x[f * spf:f * spf + N])
+            lib.check(lib.bbt_multiply_exec(B.ptr(ft), B.ptr(factor),
+                                            B.ptr(ft), ft.numel(),
+                                            _cabi.stream_ptr()))
+            back = ifft(ft)
+            result[f * spf:(f + 1) * spf] = back[self._pad_slice]
+        if out is not None:
+            if not direct:
+                out.copy_(result)
+            return out
+        if self.dtype != np.dtype(single):
+            result = result.to(B.torch_dtype(self.dtype))
+        return B.as_host(result) if host else result
+
+    def _host_phase_factor(self):
+        """`phase_factor` computed on the host in float64 and rounded to
+        complex64 (dispersion.py:115-129), shape (N or N//2+1,) + sample_shape
+        -- for the frame lengths that do not go through the fused plan."""
+        n = self._ih_samples_per_frame
+        if self._real:
+            half = self._real_phase_factor()
+            return half[self._series_map].T.reshape(
+                (n // 2 + 1,) + self.ih.sample_shape)
+        fftfreq = np.fft.fftfreq(n) * self._rate_mhz
+        f, r, s = self._chirp_par
+        d = DispersionMeasure.dispersion_delay_constant * float(self._dm)
+        table = np.empty((len(f), n), np.complex64)
+        for c in range(len(f)):
+            freq = f[c] + fftfreq * s[c]
+            phase = d * freq * (1. / r[c] - 1. / freq)**2 * 1e6 * s[c]
+            if self._sample_offset != 0:
+                phase = phase + (self._sample_offset / self._rate_mhz
+                                 * fftfreq)
+            table[c] = np.exp(phase * (2j * np.pi))
+        return table[self._series_map].T.reshape((n,) + self.ih.sample_shape)
 
     def _task_frames_real(self, data, n_frames, out, host):
         lib = _cabi.lib()

@@ -131,9 +131,51 @@ class CudaFFTBase(FFTBase):
                 pass
 
 
+def smooth_fast_len(n):
+    """Smallest length >= ``n`` with no prime factor above 7 (``n`` itself up
+    to 7): what the reference's numpy maker pads frames to
+    (fourier/numpy.py:99-126), so tasks framed with it read exactly the
+    samples per frame the reference would."""
+    n = int(n)
+    if n <= 7:
+        return n
+    best = 1 << (n - 1).bit_length()          # a power of two always qualifies
+    p7 = 1
+    while p7 < best:
+        p57 = p7
+        while p57 < best:
+            p357 = p57
+            while p357 < best:
+                # Fill up with twos.
+                rest = -(-n // p357)
+                candidate = p357 << max(0, (rest - 1).bit_length())
+                if n <= candidate < best:
+                    best = candidate
+                p357 *= 3
+            p57 *= 5
+        p7 *= 7
+    return best
+
+
 class CudaFFTMaker(FFTMakerBase):
-    """FFT factory for the hand-written CUDA kernels (key ``'cuda'``)."""
+    """FFT factory for the hand-written CUDA kernels (key ``'cuda'``).
+
+    ``fast_len='pow2'`` (default): padded tasks round their frames up to a
+    power of two, the lengths the fused kernels take.  ``fast_len='reference'``
+    (``fft_maker.set('cuda', fast_len='reference')``): frames are padded as the
+    reference's numpy maker pads them (2-3-5-7-smooth lengths), for results on
+    identical framing; such frames run through the general FFT plans
+    (Bluestein) at several times the cost.
+    """
     _FFTBase = CudaFFTBase
+
+    def __init__(self, fast_len='pow2'):
+        if fast_len not in ('pow2', 'reference'):
+            raise ValueError("fast_len should be 'pow2' or 'reference'.")
+        self._repr_kwargs = {} if fast_len == 'pow2' else {
+            'fast_len': fast_len}
+        if fast_len == 'reference':
+            self.next_fast_len = smooth_fast_len
 
     def __call__(self, shape, dtype, direction='forward', axis=0, ortho=False,
                  sample_rate=None):

@@ -107,6 +107,12 @@ int bbt_power_exec(const void* in, void* out, int64_t a, int64_t b,
                    void* stream);
 int bbt_square_exec(const void* in, void* out, int64_t n, int is_complex,
                     void* stream);
+/* out[i] = a[i] * b[i] for n complex64 values: the ``ft *= phase_factor`` of
+ * Disperse.task (dispersion.py:137) when the frame length is not one the
+ * fused dedispersion plan takes (a power of two) and the three steps run
+ * through the FFT plans. */
+int bbt_multiply_exec(const void* a, const void* b, void* out, int64_t n,
+                      void* stream);
 
 /* ---- Fused Channelize(n) -> Power: replaces channelize.py:73-74 followed by
  * functions.py:132-143 for input [(n_spec*n)][m][2] complex64 -> output

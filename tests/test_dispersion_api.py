@@ -101,3 +101,47 @@ def test_disperse_negative_dm_and_close(bt):
     disperse.close()
     with pytest.raises(ValueError):
         disperse.read(1)
+
+
+@pytest.mark.parametrize('reference_frequency', [None, 300.064e6, 299.872e6])
+def test_reference_framing(bt, reference_frequency):
+    """With ``fft_maker.set('cuda', fast_len='reference')`` frames are padded
+    like the reference's numpy maker pads them, so the default framing is the
+    reference's own: samples_per_frame 19324 or 19200 (its known answer,
+    tests/test_dispersion.py:64-69), and the samples agree with the oracle
+    on that framing."""
+    import bbt_oracle as orc
+    from test_kernels import assert_voltage
+    from baseband_tasks_b200.fourier import fft_maker
+    from baseband_tasks_b200.fourier.cuda import smooth_fast_len
+    for n in (1, 7, 8, 130, 4095, 19324 + 6400, 24000, 100003):
+        assert smooth_fast_len(n) == orc.next_fast_len(n)
+    assert smooth_fast_len(130) == 135          # tests/test_base.py:522-537
+    gp = giant_pulse(bt)
+    with fft_maker.set('cuda', fast_len='reference'):
+        dd = bt.Disperse(gp, DM, reference_frequency=reference_frequency)
+    assert dd.samples_per_frame in (19324, 19200)
+    n = dd._ih_samples_per_frame
+    assert n & (n - 1) and n == orc.next_fast_len(n)
+    x = np.zeros((164000, 2), 'c8')
+    x[GP_SAMPLE] = 1.
+    fref = None if reference_frequency is None else reference_frequency / 1e6
+    op = orc.DispersePlan(DM, 300., np.array([1, -1]), RATE / 1e6, True,
+                          164000, 1000, (2,), reference_frequency_mhz=fref)
+    assert (op.N, op.samples_per_frame) == (n, dd.samples_per_frame)
+    want = orc.disperse(x, op)
+    got = dd.read()
+    assert got.shape == want.shape
+    # A single unit sample: judged against the peak of the smeared pulse.
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # Real-valued stream on the same framing (rfft / irfft route).
+    rng = np.random.default_rng(12)
+    r = rng.normal(size=(60000,)).astype('f4')
+    src = bt.ArrayStream(r, start_time(bt), RATE, samples_per_frame=1000,
+                         frequency=300e6, sideband=1)
+    with fft_maker.set('cuda', fast_len='reference'):
+        dr = bt.Disperse(src, DM / 8)
+    opr = orc.DispersePlan(DM / 8, 300., 1, RATE / 1e6, False, 60000, 1000, ())
+    assert (opr.N, opr.samples_per_frame) == (dr._ih_samples_per_frame,
+                                              dr.samples_per_frame)
+    assert_voltage(dr.read(), orc.disperse(r, opr).astype('f4'))
