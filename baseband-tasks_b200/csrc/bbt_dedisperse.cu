@@ -179,6 +179,24 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
       return check_launch("dedispersion row kernel");
     }
   }
+  if constexpr (!PLANAR && !HALF) {
+    // Interleaved rows whose series all fit one tile: whole rows by bulk
+    // copies (dd_rowi_tma_kernel).
+    if (a.S <= C::G && C::G % a.S == 0 && tune("rowi_tma", 0) &&
+        !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
+      constexpr size_t kTile = (size_t)C::N * C::G * sizeof(cf);
+      const size_t smem =
+          (C::SMEM_BYTES > kTile ? C::SMEM_BYTES : kTile) + sizeof(Mbar);
+      auto kern = dd_rowi_tma_kernel<C>;
+      if (BBT_SET_SMEM(kern, smem))
+        return fail(BBT_ECUDA, "cannot set shared memory size");
+      const int64_t tiles = ceil_div(n1, C::G / a.S) * n_frames;
+      const int64_t ctas = std::min<int64_t>(tiles, (int64_t)sm_count());
+      prof_next_name = "dd_row";
+      BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a);
+      return check_launch("dedispersion row kernel");
+    }
+  }
   if constexpr (PLANAR && !HALF) {
     // Persistent CTAs fed by bulk copies (one tile = one contiguous range).
     if (tune("row_tma", 1) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
@@ -302,7 +320,13 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     p->planar = planar ? 1 : 0;
     // Interleaved rows run as two 64 KB tiles per SM (measured: a little
     // faster than one 128 KB tile); bit 14 of the hint switches that off.
-    if (!planar && !((hint >> 14) & 1)) p->half |= 2;
+    // ... unless a whole row (all series) fits one 512-thread tile: those go
+    // by bulk copies (dd_rowi_tma_kernel).
+    // Off by default: measured slower than two half tiles per SM (C2: 3.01
+    // against 2.26 ms per 32 frames).
+    const bool whole_rows = n_series <= 16 && 16 % n_series == 0 &&
+                            tune("rowi_tma", 0);
+    if (!planar && !((hint >> 14) & 1) && !whole_rows) p->half |= 2;
   }
   // Long contiguous rows: the formulation with warp-local sub-transforms.
   p->row2 = p->log2n1 > 0 && p->planar && p->log2n2 >= 11 && !(p->half & 2) &&

@@ -486,6 +486,119 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
   }
 }
 
+// Pass 2 for the interleaved layout, fed by bulk copies: a tile is `rpc`
+// consecutive rows with all S series (rpc S = G lanes), one contiguous range
+// of G N2 values; lanes are (row, series) pairs with the series fastest, as the
+// data lie in memory.  Otherwise as dd_row_tma_kernel.
+template <class C>
+BBT_DEV_NOINLINE void dd_rowi_tma_tile(
+    cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw, int S,
+    bool valid, unsigned phase, const char* next_src, unsigned next_bytes) {
+  const int tid = threadIdx.x;
+  const int g = tid % C::G, t = tid / C::G;
+  const int kl = g / S, sl = g - kl * S;
+  constexpr unsigned kChunk = 32 * 1024;
+  mbar_wait(bar, phase & 1u, phase);
+  cf v[C::E];
+  {
+    const cf* land = smem + ((size_t)kl * C::N + t) * S + sl;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      v[e] = valid ? land[(size_t)C::T * e * S] : mk(0.f, 0.f);
+  }
+  BBT_SYNC();  // the landing zone becomes the exchange buffer
+  SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
+  block_fft<C>(v, t, tw, sm);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < C::E; ++e)
+      v[e] = cconj(cmul(v[e], ldtw(chirp, t + C::T * e)));
+  }
+  block_fft_head<C>(v, t, tw, sm);
+  if (tid == 0 && next_bytes) {
+    fence_proxy_async();
+    mbar_expect_tx(bar, next_bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < next_bytes; o += kChunk)
+      bulk_load(dst + o, next_src + o,
+                next_bytes - o < kChunk ? next_bytes - o : kChunk, bar,
+                o + kChunk >= next_bytes);
+  }
+  block_fft_tail<C>(v, t, tw, sm);
+  if (valid) {
+    cf* out = row + (size_t)t * S;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) out[(size_t)C::T * e * S] = v[e];
+  }
+}
+
+template <class C>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_rowi_tma_kernel(DdArgs a) {
+  cf* smem = BBT_SMEM(cf);
+  constexpr size_t kTile = (size_t)C::N * C::G;
+  constexpr size_t kBuf = C::SMEM_BYTES / sizeof(cf) > kTile
+                              ? C::SMEM_BYTES / sizeof(cf) : kTile;
+  Mbar* bar = reinterpret_cast<Mbar*>(smem + kBuf);
+  const unsigned n1 = (unsigned)(a.N >> a.log2n2);
+  const int S = (int)a.S;
+  const unsigned rpc = C::G / S;                     // rows per tile
+  const unsigned tiles_per_frame = (n1 + rpc - 1) / rpc;
+  const unsigned n_tiles = tiles_per_frame * (unsigned)a.n_frames;
+  const int tid = threadIdx.x;
+  const int g = tid % C::G;
+  const unsigned kl = g / S, sl = g - kl * S;
+  constexpr unsigned kChunk = 32 * 1024;
+  auto tile_base = [&](unsigned lin, unsigned& k10) -> cf* {
+    const unsigned xblk = lin / (unsigned)a.n_frames;
+    const unsigned frame = lin - xblk * (unsigned)a.n_frames;
+    k10 = xblk * rpc;
+    return a.work + (long long)frame * a.N * a.S +
+           (long long)k10 * C::N * a.S;
+  };
+  auto tile_bytes = [&](unsigned k10) -> unsigned {
+    const unsigned left = n1 - k10;
+    return (left < rpc ? left : rpc) * C::N * (unsigned)S *
+           (unsigned)sizeof(cf);
+  };
+  if (tid == 0) mbar_init(bar, 1);
+  BBT_SYNC();
+  if (tid == 0 && blockIdx.x < n_tiles) {
+    unsigned k10;
+    const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, k10));
+    const unsigned bytes = tile_bytes(k10);
+    mbar_expect_tx(bar, bytes);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < bytes; o += kChunk)
+      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
+                o + kChunk >= bytes);
+  }
+  unsigned k = 0;
+#pragma unroll 1
+  for (unsigned lin = blockIdx.x; lin < n_tiles; lin += gridDim.x, ++k) {
+    unsigned k10;
+    cf* base = tile_base(lin, k10);
+    const unsigned k1 = k10 + kl;
+    const bool valid = k1 < n1;
+    cf* row = base + (long long)kl * C::N * a.S + sl;
+    const cf* chirp = a.chirp;
+    if (valid) chirp += ((long long)a.series_map[sl] * n1 + k1) * C::N;
+    const unsigned next = lin + gridDim.x;
+    const char* next_src = nullptr;
+    unsigned next_bytes = 0;
+    if (next < n_tiles) {
+      unsigned r0;
+      next_src = reinterpret_cast<const char*>(tile_base(next, r0));
+      next_bytes = tile_bytes(r0);
+      if (tid == 32)
+        for (unsigned o = 0; o < next_bytes; o += kChunk)
+          bulk_prefetch_l2(next_src + o,
+                           next_bytes - o < kChunk ? next_bytes - o : kChunk);
+    }
+    dd_rowi_tma_tile<C>(smem, bar, row, chirp, a.tw, S, valid, k, next_src,
+                        next_bytes);
+  }
+}
+
 // Pass 2, second formulation: the N2-point transforms are split as 32 x M
 // (M = N2/32) so that only ONE exchange per transform needs the whole CTA.
 //   forward:  radix-32 butterflies over e of x[u + M e] in the thread that
