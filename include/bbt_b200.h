@@ -73,7 +73,9 @@ int bbt_fft_plan_destroy(bbt_fft_plan* plan);
  * log2 of the column-FFT length, bit 8 / 9: force the planar / interleaved
  * work-buffer layout, bits 12 / 13: half-size (two per SM) tiles in the
  * column / row passes, bit 14: full-size row tiles for the interleaved
- * layout (tuning and tests). */
+ * layout (tuning and tests).  Which kernel variants run (persistent kernels
+ * fed by bulk / tensor-map copies, row formulations) is the library's choice;
+ * bbt_tune_set can force them for A/B measurements. */
 int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
                                int64_t n_series, int64_t pad_start,
                                int64_t n_valid, int64_t n_chirp,
@@ -89,6 +91,10 @@ int bbt_dedisperse_plan_set_response(bbt_dedisperse_plan* plan,
 /* Copy the chirp back to the host in natural bin order ([n_chirp][n]). */
 int bbt_dedisperse_plan_get_response(const bbt_dedisperse_plan* plan,
                                      void* host_response);
+/* Bytes of scratch bbt_dedisperse_exec needs for a run of n_frames frames
+ * (the three-pass work buffer plus the tile counters of the persistent
+ * column passes; 0 for single-pass plans).  The buffer is the caller's, 16-byte
+ * aligned, and must not be shared by calls that run concurrently. */
 int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* plan,
                                   int64_t n_frames);
 /* Frame f reads in + f*in_frame_stride (complex elements) and writes its
