@@ -67,6 +67,9 @@ int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
     if (tune("chanpow_e16", 0))   // 16 values per thread, twice the warps
       return launch_chanpow_cfg<FftCfg<10, 4, 512>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
+    if (tune("chanpow_g4", 0))    // half-size tiles, two CTAs per SM
+      return launch_chanpow_cfg<FftCfg<10, 5, 128>, INTEGRATE>(a, n_bins,
+                                                               max_width, st);
     return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
                                                              max_width, st);
   }
@@ -79,7 +82,7 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st) {
   constexpr int64_t units = C::G / 2;  // (sub-stream, m) pairs per CTA
   // Sub-streams per bin so that the grid fills the GPU a few times over.
-  const int64_t want = (int64_t)sm_count() * 4 * units;
+  const int64_t want = (int64_t)sm_count() * tune("chanpow_waves", 4) * units;
   int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));
   // Whole tiles of sub-streams: a CTA of the bulk-copy kernel takes
   // units / M adjacent spectra at a time.
@@ -295,6 +298,20 @@ int launch_pfb(const PfbArgs& a, int kind, bbt_stream_t st) {
       return fail(BBT_ECUDA, "cannot set shared memory size");
     prof_next_name = "pfb";
     BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a);
+    return check_launch("polyphase filter bank kernel");
+  }
+  if (kind != 0 && a.inner % 2 == 0 && C::N >= 4 &&
+      !(reinterpret_cast<uintptr_t>(a.in) & (kind == 2 ? 1 : 7)) &&
+      !(reinterpret_cast<uintptr_t>(a.out) & 15) && tune("pfb_pair", 1)) {
+    // Real input, columns in pairs: one complex transform per pair.
+    const int64_t pblocks = ceil_div(a.n_spec * (a.inner / 2), C::G);
+    const size_t smem =
+        std::max<size_t>(C::SMEM_BYTES, (size_t)C::G * C::NPAD * sizeof(cf));
+    auto kern = kind == 2 ? pfb_pair_kernel<C, 2> : pfb_pair_kernel<C, 1>;
+    if (BBT_SET_SMEM(kern, smem))
+      return fail(BBT_ECUDA, "cannot set shared memory size");
+    prof_next_name = "pfb";
+    BBT_LAUNCH(kern, dim3((unsigned)pblocks), dim3(C::THREADS), smem, st, a);
     return check_launch("polyphase filter bank kernel");
   }
   const size_t smem = C::SMEM_BYTES;

@@ -24,6 +24,39 @@ BBT_HD f4 stokes_like(cf a, cf b) {
   return r;
 }
 
+// The same four products accumulated for a polarization pair whose halves sit
+// in two threads: each keeps one value (`keep`, its own polarization) and is
+// sent the partner's (`other`).  Which of the two is X depends on the thread,
+// but |keep|^2, |other|^2 and Re(keep conj other) do not care and
+// Im(keep conj other) only changes sign, so the sums are formed the same way
+// in both threads (no selects in the loop) and put in order once at the end
+// (stokes_finish).  acc = [sum |keep|^2, sum |other|^2, sum Re, sum Im]; the
+// two squares share packed multiply-adds.
+BBT_HD void stokes_accumulate(f4& acc, cf keep, cf other) {
+#if defined(BBT_PACKED)
+  cf pw = mk(acc.x, acc.y);
+  pw = u2(fma2(p2(keep.x, other.x), p2(keep.x, other.x), p2(pw)));
+  pw = u2(fma2(p2(keep.y, other.y), p2(keep.y, other.y), p2(pw)));
+  acc.x = pw.x;
+  acc.y = pw.y;
+#else
+  acc.x = fmaf(keep.y, keep.y, fmaf(keep.x, keep.x, acc.x));
+  acc.y = fmaf(other.y, other.y, fmaf(other.x, other.x, acc.y));
+#endif
+  acc.z = fmaf(keep.y, other.y, fmaf(keep.x, other.x, acc.z));
+  acc.w = fmaf(-keep.x, other.y, fmaf(keep.y, other.x, acc.w));
+}
+// keep = Y, other = X (p = 1): swap the squares, Im(X conj Y) = -Im(Y conj X).
+BBT_HD f4 stokes_finish(f4 acc, int p) {
+  f4 r = acc;
+  if (p) {
+    r.x = acc.y;
+    r.y = acc.x;
+    r.w = -acc.w;
+  }
+  return r;
+}
+
 // (A, 2, B) complex -> (A, 4, B) float.
 BBT_GLOBAL void power_kernel(const cf* BBT_RESTRICT in, float* BBT_RESTRICT out,
                              long long A, long long B) {
@@ -203,13 +236,10 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
       cf other;
       other.x = shfl_xor1(send.x);
       other.y = shfl_xor1(send.y);
-      const f4 q = p ? stokes_like(other, mine) : stokes_like(mine, other);
       if (INTEGRATE) {
-        acc[i].x += q.x;
-        acc[i].y += q.y;
-        acc[i].z += q.z;
-        acc[i].w += q.w;
+        stokes_accumulate(acc[i], mine, other);
       } else if (valid) {
+        const f4 q = p ? stokes_like(other, mine) : stokes_like(mine, other);
         const int k = t + C::T * (2 * i + p);
         reinterpret_cast<f4*>(a.out)[(j * C::N + k) * a.M + m] = q;
       }
@@ -225,10 +255,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
       for (int i = 0; i < C::E / 2; ++i) {
         const int k = t + C::T * (2 * i + p);
         float* o = a.out + ((b * C::N + k) * a.M + m) * 4;
-        atomic_add(o + 0, acc[i].x / w);
-        atomic_add(o + 1, acc[i].y / w);
-        atomic_add(o + 2, acc[i].z / w);
-        atomic_add(o + 3, acc[i].w / w);
+        const f4 q = stokes_finish(acc[i], p);
+        atomic_add(o + 0, q.x / w);
+        atomic_add(o + 1, q.y / w);
+        atomic_add(o + 2, q.z / w);
+        atomic_add(o + 3, q.w / w);
       }
     }
     if (tid == 0 && blockIdx.x == 0 && hi > lo)
@@ -351,11 +382,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
       cf other;
       other.x = shfl_xor1(send.x);
       other.y = shfl_xor1(send.y);
-      const f4 q = p ? stokes_like(other, keep) : stokes_like(keep, other);
-      acc[i].x += q.x;
-      acc[i].y += q.y;
-      acc[i].z += q.z;
-      acc[i].w += q.w;
+      stokes_accumulate(acc[i], keep, other);
     }
   }
   if (lane_ok && hi > lo) {
@@ -365,10 +392,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
     for (int i = 0; i < C::E / 2; ++i) {
       const int k = t + C::T * (2 * i + p);
       float* o = a.out + ((b * C::N + k) * a.M + m) * 4;
-      atomic_add(o + 0, acc[i].x / w);
-      atomic_add(o + 1, acc[i].y / w);
-      atomic_add(o + 2, acc[i].z / w);
-      atomic_add(o + 3, acc[i].w / w);
+      const f4 q = stokes_finish(acc[i], p);
+      atomic_add(o + 0, q.x / w);
+      atomic_add(o + 1, q.y / w);
+      atomic_add(o + 2, q.z / w);
+      atomic_add(o + 3, q.w / w);
     }
   }
   if (tid == 0 && blockIdx.x == 0 && hi > lo)
@@ -943,6 +971,77 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
     for (int e = 0; e < C::E; ++e) {
       const int k = t + C::T * e;
       if (!REAL || k <= C::N / 2) dst[k * a.inner] = v[e];
+    }
+  }
+}
+
+// Real input with an even number of columns: two adjacent columns (for a
+// baseband stream, the two polarizations) are filtered and transformed as ONE
+// complex series z = x_a + i x_b -- the pair of 8-bit samples or floats in
+// memory IS that complex number -- and the two spectra are taken apart after
+// the transform (A[k] = (Z[k] + conj Z[n-k]) / 2, B[k] = (Z[k] - conj Z[n-k])
+// / 2i), which costs one more pass through shared memory but half the
+// transforms, half the filter loads and half the exchanges of pfb_kernel.
+// Lanes are (spectrum, column pair) with the pair fastest; the threads of a
+// lane are consecutive (SmemLaneSlow), so a warp reads 32 adjacent sample
+// pairs and stores 32 adjacent channels of both columns (512 bytes).
+template <class C, int KIND>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    pfb_pair_kernel(PfbArgs a) {
+  static_assert(KIND == 1 || KIND == 2, "real input");
+  cf* smem = BBT_SMEM(cf);
+  const int tid = threadIdx.x;
+  const int t = tid % C::T, g = tid / C::T;
+  const long long pairs = a.inner / 2;
+  const long long lane = (long long)blockIdx.x * C::G + g;
+  const long long j = lane / pairs, cp = lane - j * pairs;
+  const bool valid = j < a.n_spec;
+  cf v[C::E];
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) v[e] = mk(0.f, 0.f);
+  if (valid) {
+    for (int tap = 0; tap < a.n_tap; ++tap) {
+      const float* h = a.h + (long long)tap * C::N + t;
+      const long long base = ((j + tap) * C::N + t) * a.inner + 2 * cp;
+      const long long step = (long long)C::T * a.inner;
+#pragma unroll
+      for (int e = 0; e < C::E; ++e) {
+        const float w = BBT_LDGF(h + C::T * e);
+        if (KIND == 2) {
+          const short two = *reinterpret_cast<const short*>(
+              static_cast<const signed char*>(a.in) + base + e * step);
+          v[e].x = fmaf(w, (float)(signed char)(two & 0xff), v[e].x);
+          v[e].y = fmaf(w, (float)(signed char)(two >> 8), v[e].y);
+        } else {
+          const cf x = *reinterpret_cast<const cf*>(
+              static_cast<const float*>(a.in) + base + e * step);
+          v[e].x = fmaf(w, x.x, v[e].x);
+          v[e].y = fmaf(w, x.y, v[e].y);
+        }
+      }
+    }
+  }
+  cf* z = smem + (size_t)g * C::NPAD;
+  SmemLaneSlow<C::PADSHIFT> sm{z};
+  block_fft<C>(v, t, a.tw, sm);
+#pragma unroll
+  for (int e = 0; e < C::E; ++e) z[t + C::T * e] = v[e];
+  BBT_SYNC();
+  if (valid) {
+    const long long n_chan = C::N / 2 + 1;
+    f4* dst = reinterpret_cast<f4*>(a.out + (j * n_chan) * a.inner + 2 * cp);
+#pragma unroll
+    for (int r = 0; r <= C::E / 2; ++r) {
+      const int k = t + C::T * r;
+      if (k <= C::N / 2) {
+        const cf zk = z[k], zm = z[(C::N - k) & (C::N - 1)];
+        f4 q;
+        q.x = 0.5f * (zk.x + zm.x);
+        q.y = 0.5f * (zk.y - zm.y);
+        q.z = 0.5f * (zk.y + zm.y);
+        q.w = 0.5f * (zm.x - zk.x);
+        dst[k * pairs] = q;
+      }
     }
   }
 }

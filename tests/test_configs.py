@@ -268,3 +268,76 @@ def test_bench_block_shape(bt, which):
         wsum = power.reshape((b1 - b0, 8) + power.shape[1:]).sum(1)
         assert np.all(spectra['count'][b0:b1] == 8)
         assert_power(spectra['data'][b0:b1], wsum)
+
+
+def test_c4_time_block_sharding(bt):
+    """configs[3] shared out in time: two ranks' blocks (frames plus the
+    overlap-save halo, `parallel.StreamBlock`) processed one after the other
+    on this GPU give, after adding the partial sums of the bin the cut runs
+    through, exactly the counts and (to 1e-5) the sums of the whole stream;
+    with Fold the phase bins are bit-identical."""
+    from baseband_tasks_b200 import parallel
+    rate, freq, dm, N = 512e6, 8192e6, 1000., 1 << 24
+    pads = (1889551, 2075345)
+    spf, pad = N - sum(pads), sum(pads)
+    n_frames, world = 3, 2
+    n = n_frames * spf + pad
+    g = np.random.default_rng(777)
+    x = np.empty((n, 2), np.complex64)
+    xv = x.view(np.float32)
+    for i in range(0, n, 1 << 22):
+        xv[i:i + (1 << 22)] = g.standard_normal(xv[i:i + (1 << 22)].shape,
+                                                dtype=np.float32)
+    kw = dict(frequency=freq, sideband=1, polarization=np.array(['X', 'Y']))
+
+    def chain(src, fold):
+        dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+        if fold:
+            poly = bt.PolynomialPhase([0.25, 29.946923e3, -3.77535e-4 / 2.],
+                                      t0(bt))
+            return bt.Fold(bt.Power(dd), 512, poly, average=False)
+        return bt.Integrate(bt.Power(bt.Channelize(dd, 1024)), 1e-3,
+                            average=False)
+
+    whole = bt.ArrayStream(bt._buffers.as_device(x), t0(bt), rate,
+                           samples_per_frame=1 << 20, **kw)
+    for fold in (False, True):
+        unit = 1 if fold else 1024
+        ref = chain(whole, fold)
+        plans = [parallel.block_plan(n_frames, spf, pad, unit, r, world)
+                 for r in range(world)]
+        assert plans[0][1] == plans[1][0] and plans[0][0] == 0
+        total_s = total_c = None
+        for first, last, in0, in1 in plans:
+            block = parallel.StreamBlock(
+                bt._buffers.as_device(x[in0:in1]), in0, n, t0(bt), rate,
+                samples_per_frame=1 << 20, **kw)
+            it = chain(block, fold)
+            assert it.shape == ref.shape
+            if fold:
+                it.seek(0)
+                s, c = it.read_sums(within=(first, last))
+            else:
+                edges = it._get_offsets(np.arange(it.shape[0] + 1))
+                b0, b1 = parallel.bin_range(edges, first // unit, last // unit)
+                it.seek(b0)
+                part = it.read_sums(b1 - b0, within=(first // unit,
+                                                     last // unit))
+                s = part[0].new_zeros((it.shape[0],) + part[0].shape[1:])
+                c = part[1].new_zeros((it.shape[0],) + part[1].shape[1:])
+                s[b0:b1], c[b0:b1] = part
+            total_s = s if total_s is None else total_s + s
+            total_c = c if total_c is None else total_c + c
+        ref.seek(0)
+        n_whole = plans[-1][1] // unit          # complete frames only
+        if fold:
+            rs, rc = ref.read_sums(within=(0, plans[-1][1]))
+        else:
+            rs, rc = ref.read_sums()
+            edges = ref._get_offsets(np.arange(ref.shape[0] + 1))
+            full = edges[1:] <= n_whole
+            rs, rc = rs[full], rc[full]
+            total_s, total_c = total_s[full], total_c[full]
+        np.testing.assert_array_equal(total_c.cpu().numpy(),
+                                      rc.cpu().numpy())
+        assert_power(total_s.cpu().numpy(), rs.cpu().numpy())

@@ -598,6 +598,7 @@ def test_sinc_hamming_guppi(bt):
 
 
 @pytest.mark.parametrize('dtype,shape', [('f4', ()), ('f4', (2,)),
+                                         ('f4', (3,)), ('f4', (2, 2)),
                                          ('c8', (3,))])
 def test_polyphase_filter_bank(bt, dtype, shape):
     """tests/test_pfb.py:54-102 (single precision): the filter bank equals
