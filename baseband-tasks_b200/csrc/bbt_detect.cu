@@ -67,9 +67,17 @@ int launch_chanpow(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
     if (tune("chanpow_e16", 0))   // 16 values per thread, twice the warps
       return launch_chanpow_cfg<FftCfg<10, 4, 512>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
-    if (tune("chanpow_g4", 0))    // half-size tiles, two CTAs per SM
+    // Narrow samples (one or two polarization pairs, the bulk-copy kernel):
+    // 4 lanes per CTA, so that two CTAs share an SM and one runs its
+    // butterflies while the other waits at a barrier or for its tile
+    // (C4, per 32 frames: 8 lanes 2.11 ms, 4 lanes 1.64 ms).
+    const int lanes = tune("chanpow_g", a.M <= 2 ? 4 : 8);
+    if (lanes == 4)
       return launch_chanpow_cfg<FftCfg<10, 5, 128>, INTEGRATE>(a, n_bins,
                                                                max_width, st);
+    if (lanes == 2)
+      return launch_chanpow_cfg<FftCfg<10, 5, 64>, INTEGRATE>(a, n_bins,
+                                                              max_width, st);
     return launch_chanpow_cfg<FftCfg<10, 5, 256>, INTEGRATE>(a, n_bins,
                                                              max_width, st);
   }
@@ -82,7 +90,9 @@ int launch_chanpow_cfg(ChanPowArgs& a, int64_t n_bins, int64_t max_width,
                        bbt_stream_t st) {
   constexpr int64_t units = C::G / 2;  // (sub-stream, m) pairs per CTA
   // Sub-streams per bin so that the grid fills the GPU a few times over.
-  const int64_t want = (int64_t)sm_count() * tune("chanpow_waves", 4) * units;
+  // (Eight CTAs' worth per SM: with four, the last wave of a long launch
+  // left a tenth of the time to a partly idle GPU.)
+  const int64_t want = (int64_t)sm_count() * tune("chanpow_waves", 8) * units;
   int64_t msub = ceil_div(want, a.M * (INTEGRATE ? n_bins : 1));
   // Whole tiles of sub-streams: a CTA of the bulk-copy kernel takes
   // units / M adjacent spectra at a time.
