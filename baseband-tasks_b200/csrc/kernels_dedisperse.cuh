@@ -678,12 +678,38 @@ struct ChirpRegen {          // per row: what chirp_value needs
   int log2n2;
 };
 
+#ifndef BBT_ROW_FLAGS
+// dd_row2_kernel: bit 0, groups of warps take turns at shared memory after a
+// barrier (stagger_in); bit 1, the barrier between the landing zone's reads
+// and the first exchange comes after the butterflies; bit 2, only the warp
+// that issues the next tile's copy waits for the last reads of a tile.
+#define BBT_ROW_FLAGS 1
+#endif
+// After a CTA-wide barrier every warp wants shared memory (the reads of an
+// exchange) and then the FP32 pipe (its butterflies): with fair scheduling the
+// warps move through these phases together, and the pipe idles while shared
+// memory is busy and vice versa.  Here the CTA's warps form four groups (warp
+// w in group w / 4 of the n = THREADS / 128, so that every scheduler has one
+// warp of each) which issue their loads one group after the other: the first
+// group is at its butterflies while the others still load, and the skew stays
+// for the phases that follow.  Barriers 1.. chain the groups.
+BBT_DEV void stagger_in(int grp, int flags) {
+  if ((flags & 1) && grp > 0) named_bar_sync(grp, 256);
+}
+BBT_DEV void stagger_out(int grp, int n_grp, int flags) {
+  if ((flags & 1) && grp + 1 < n_grp) named_bar_arrive(grp + 1, 256);
+}
+
 template <class C, bool REGEN>
 BBT_DEV_NOINLINE void dd_row2_tile(
     cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw,
     const cf* tw_sub, bool valid, unsigned phase, const char* next_src,
     unsigned next_bytes, const ChirpRegen* rg) {
   static_assert(C::LOG2E == 5 && C::LOG2N >= 10, "32 values per thread");
+  constexpr int flags = BBT_ROW_FLAGS;
+  static_assert(C::THREADS % 128 == 0, "groups of four warps");
+  constexpr int kGroups = C::THREADS / 128;
+  const int grp = threadIdx.x / 128;
   using R = Row2Cfg<C>;
   using CS = typename R::CS;
   constexpr int M = R::M, Ts = R::Ts, P = R::P;
@@ -698,22 +724,29 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   const cf* tab_sub = tab_outer + R::kTabOuter;
   mbar_wait(bar, phase & 1u, phase);
   cf v[32];
+  stagger_in(grp, flags);
   {
     const cf* land = smem + g * C::N + u;
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = valid ? land[M * e] : mk(0.f, 0.f);
   }
-  BBT_SYNC();  // the landing zone becomes the exchange buffer
+  stagger_out(grp, kGroups, flags);
+  // The landing zone becomes the exchange buffer once every thread has taken
+  // its values; the butterflies in between need registers only.
+  if (!(flags & 2)) BBT_SYNC();
   // Forward: over e in this thread, twiddle, transpose.
   Dft<32>::run(v);
   apply_twiddles_tab<32>(v, tab_outer, M, u);
+  if (flags & 2) BBT_SYNC();
 #pragma unroll
   for (int r = 0; r < 32; ++r) X[r * P + u] = v[r];
   BBT_SYNC();
   // From here to the next barrier warps do not wait for one another.
   cf* mine = X + k1 * P;
+  stagger_in(grp, flags);
 #pragma unroll
   for (int e = 0; e < 32; ++e) v[e] = mine[tt + Ts * e];
+  stagger_out(grp, kGroups, flags);
   BBT_SYNCWARP();
   SmemWarp<CS::PADSHIFT> sw{mine, tab_sub};
   block_fft<CS>(v, tt, tw_sub, sw);
@@ -746,10 +779,26 @@ BBT_DEV_NOINLINE void dd_row2_tile(
 #pragma unroll
   for (int e = 0; e < 32; ++e) mine[tt + Ts * e] = v[e];
   BBT_SYNC();
+  stagger_in(grp, flags);
 #pragma unroll
   for (int r = 0; r < 32; ++r) v[r] = X[r * P + u];
-  BBT_SYNC();  // X is free: the next tile may land while we finish
-  if (tid == 0 && next_bytes) {
+  stagger_out(grp, kGroups, flags);
+  // X is free once every thread has read: the next tile may land while we
+  // finish.  Only the warp that issues the copy (the last one, whose group
+  // reads last) has to wait for that; the others go on to their butterflies.
+#if defined(BBT_EMULATE)
+  BBT_SYNC();
+#else
+  if constexpr ((flags & 4) != 0) {
+    if (tid >= C::THREADS - 32)
+      named_bar_sync(8, C::THREADS);
+    else
+      named_bar_arrive(8, C::THREADS);
+  } else {
+    BBT_SYNC();
+  }
+#endif
+  if (tid == ((flags & 4) ? C::THREADS - 32 : 0) && next_bytes) {
     fence_proxy_async();
     mbar_expect_tx(bar, next_bytes);
     char* dst = reinterpret_cast<char*>(smem);

@@ -54,6 +54,11 @@ inline void bulk_commit() {}
 inline void bulk_wait_read0() {}
 inline void bulk_wait_all0() {}
 inline void bulk_prefetch_l2(const void*, uint32_t) {}
+// Named barriers (bar.sync / bar.arrive with an id and a thread count): only
+// orderings between groups of warps that help performance are expressed with
+// them, so the emulation needs nothing for them.
+inline void named_bar_sync(int, int) {}
+inline void named_bar_arrive(int, int) {}
 inline void tensor_prefetch_2d(const TensorMap*, int, int) {}
 inline void tensor_prefetch_3d(const TensorMap*, int, int, int) {}
 inline void tensor_copy_emu(const TensorMap* m, void* smem, const int* c,
@@ -111,6 +116,15 @@ namespace bbt {
 typedef CUtensorMap TensorMap;
 typedef unsigned long long Mbar;
 #if defined(__CUDACC__)
+// Named barriers: `threads` (a multiple of 32) threads of the CTA take part,
+// arriving (not waiting) or synchronising (waiting) on barrier `id` (1-15;
+// 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }
