@@ -43,6 +43,10 @@ _SIGNATURES = {
     'bbt_dedisperse_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_void_p, c_int64, c_void_p,
                                     c_void_p]),
+    'bbt_dedisperse_power_supported': (c_int, [c_void_p]),
+    'bbt_dedisperse_power_exec': (c_int, [c_void_p, c_void_p, c_int64,
+                                          c_int64, c_int64, c_void_p, c_int64,
+                                          c_void_p, c_void_p]),
     'bbt_dedisperse_plan_destroy': (c_int, [c_void_p]),
     'bbt_power_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int64,
                                c_void_p]),

@@ -127,7 +127,12 @@ int launch_dd_col(bool inverse, const DdArgs& a0, int64_t n_frames,
   DdArgs a = a0;
   if (HALF) a.ahead *= 2;
   const int64_t cols = (a.N >> L1) * a.S;
-  if (tune("col_tma", 1)) {
+  // (Fused power, planar source: the two polarizations of a sample must sit
+  // in one warp, G / S <= 16 lanes apart; else the per-thread-load kernel,
+  // whose lanes are flat columns.)
+  const bool far_pairs = inverse && a.detect && a.planar && a.S <= C::G &&
+                         C::G / a.S > 16;
+  if (tune("col_tma", 1) && !far_pairs) {
     const int rc = launch_dd_col_tma<C>(inverse, a, n_frames, st);
     if (rc != BBT_EUNSUPPORTED) return rc;  // else: the per-thread-load kernels
   }
@@ -470,14 +475,13 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
                                int64_t in_frame_stride, int64_t n_frames,
                                int64_t skip, void* out,
                                int64_t out_frame_stride, void* work,
-                               void* stream);
+                               void* stream, int detect);
 
-extern "C" {
-
-int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
-                        int64_t in_frame_stride, int64_t n_frames,
-                        int64_t skip, void* out, int64_t out_frame_stride,
-                        void* work, void* stream) {
+static int dedisperse_exec_all(const bbt_dedisperse_plan* p, const void* in,
+                               int64_t in_frame_stride, int64_t n_frames,
+                               int64_t skip, void* out,
+                               int64_t out_frame_stride, void* work,
+                               void* stream, int detect) {
   if (!p || !in || !out) return fail(BBT_EINVAL, "null argument");
   if (n_frames <= 0) return BBT_OK;
   if (skip < 0 || skip >= p->n_valid) return fail(BBT_EINVAL, "bad skip");
@@ -488,10 +492,39 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
     const int rc = dedisperse_exec_run(
         p, static_cast<const cf*>(in) + f0 * in_frame_stride, in_frame_stride,
         nf, skip, static_cast<cf*>(out) + f0 * out_frame_stride,
-        out_frame_stride, work, stream);
+        out_frame_stride, work, stream, detect);
     if (rc) return rc;
   }
   return BBT_OK;
+}
+
+extern "C" {
+
+int bbt_dedisperse_power_supported(const bbt_dedisperse_plan* p) {
+  // The products are formed in the last of the three passes, between the two
+  // lanes of a polarization pair.
+  return p && p->log2n1 > 0 && !(p->n_series & 1) && tune("dd_power", 1);
+}
+
+int bbt_dedisperse_power_exec(const bbt_dedisperse_plan* p, const void* in,
+                              int64_t in_frame_stride, int64_t n_frames,
+                              int64_t skip, void* out,
+                              int64_t out_frame_stride, void* work,
+                              void* stream) {
+  if (!bbt_dedisperse_power_supported(p))
+    return fail(BBT_EUNSUPPORTED,
+                "no fused power for this plan (single pass or an odd number "
+                "of series)");
+  return dedisperse_exec_all(p, in, in_frame_stride, n_frames, skip, out,
+                             out_frame_stride, work, stream, 1);
+}
+
+int bbt_dedisperse_exec(const bbt_dedisperse_plan* p, const void* in,
+                        int64_t in_frame_stride, int64_t n_frames,
+                        int64_t skip, void* out, int64_t out_frame_stride,
+                        void* work, void* stream) {
+  return dedisperse_exec_all(p, in, in_frame_stride, n_frames, skip, out,
+                             out_frame_stride, work, stream, 0);
 }
 
 }  // extern "C"
@@ -500,9 +533,10 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
                                int64_t in_frame_stride, int64_t n_frames,
                                int64_t skip, void* out,
                                int64_t out_frame_stride, void* work,
-                               void* stream) {
+                               void* stream, int detect) {
   bbt_stream_t st = as_stream(stream);
   DdArgs a;
+  a.detect = detect;
   a.in = static_cast<const cf*>(in);
   a.out = static_cast<cf*>(out);
   a.work = static_cast<cf*>(work);

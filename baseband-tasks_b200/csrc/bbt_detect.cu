@@ -286,6 +286,24 @@ int bbt_fold_exec(const void* in, int power, int64_t n, int64_t inner,
 
 }  // extern "C"
 namespace {
+// Real input, columns in pairs: one complex transform per pair
+// (pfb_pair_kernel), in CTAs of THREADS threads.
+template <int L, int THREADS>
+int launch_pfb_pair(const PfbArgs& a, int kind, bbt_stream_t st) {
+  using D = DefaultCfg<L>;
+  using C = FftCfg<L, D::LOG2E, THREADS>;
+  const int64_t blocks = ceil_div(a.n_spec * (a.inner / 2), C::G);
+  if (blocks > 2147483647LL) return fail(BBT_EUNSUPPORTED, "grid too large");
+  const size_t smem =
+      std::max<size_t>(C::SMEM_BYTES, (size_t)C::G * C::NPAD * sizeof(cf));
+  auto kern = kind == 2 ? pfb_pair_kernel<C, 2> : pfb_pair_kernel<C, 1>;
+  if (BBT_SET_SMEM(kern, smem))
+    return fail(BBT_ECUDA, "cannot set shared memory size");
+  prof_next_name = "pfb";
+  BBT_LAUNCH(kern, dim3((unsigned)blocks), dim3(C::THREADS), smem, st, a);
+  return check_launch("polyphase filter bank kernel");
+}
+
 template <int L>
 int launch_pfb(const PfbArgs& a, int kind, bbt_stream_t st) {
   using D = DefaultCfg<L>;
@@ -313,16 +331,12 @@ int launch_pfb(const PfbArgs& a, int kind, bbt_stream_t st) {
   if (kind != 0 && a.inner % 2 == 0 && C::N >= 4 &&
       !(reinterpret_cast<uintptr_t>(a.in) & (kind == 2 ? 1 : 7)) &&
       !(reinterpret_cast<uintptr_t>(a.out) & 15) && tune("pfb_pair", 1)) {
-    // Real input, columns in pairs: one complex transform per pair.
-    const int64_t pblocks = ceil_div(a.n_spec * (a.inner / 2), C::G);
-    const size_t smem =
-        std::max<size_t>(C::SMEM_BYTES, (size_t)C::G * C::NPAD * sizeof(cf));
-    auto kern = kind == 2 ? pfb_pair_kernel<C, 2> : pfb_pair_kernel<C, 1>;
-    if (BBT_SET_SMEM(kern, smem))
-      return fail(BBT_ECUDA, "cannot set shared memory size");
-    prof_next_name = "pfb";
-    BBT_LAUNCH(kern, dim3((unsigned)pblocks), dim3(C::THREADS), smem, st, a);
-    return check_launch("polyphase filter bank kernel");
+    // Real input, columns in pairs: one complex transform per pair.  Small
+    // CTAs, so that several share an SM and their barriers do not line up.
+    const int threads = tune("pfb_threads", 64);
+    if (threads == 64) return launch_pfb_pair<L, 64>(a, kind, st);
+    if (threads == 128) return launch_pfb_pair<L, 128>(a, kind, st);
+    return launch_pfb_pair<L, 256>(a, kind, st);
   }
   const size_t smem = C::SMEM_BYTES;
   auto kern = kind == 2   ? pfb_kernel<C, 2>

@@ -53,6 +53,11 @@ struct DdArgs {
   // Interleaved row tiles (set by the launcher): series per tile, rows per
   // tile, tiles per row.
   int row_sc, row_rpc, row_chunks;
+  // Power fused into the last pass (bbt_dedisperse_power_exec): series 2q and
+  // 2q+1 are the two polarizations of a pair, and instead of their voltages
+  // X, Y the output holds [|X|^2, |Y|^2, Re(X conj Y), Im(X conj Y)] as four
+  // floats in the same 16 bytes (functions.py:138-142).
+  int detect;
 };
 
 // Ask L2 for `rows` runs of `run_bytes` each, `stride_bytes` apart: the tile a
@@ -167,6 +172,26 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   }
 }
 
+// What a lane stores when Power is fused into the last pass: `mine` is its
+// voltage, the lane `d` away (lane ^ d) holds the other polarization of the
+// same sample.  The first lane of a pair (X) returns [|X|^2, |Y|^2], the
+// second (Y) [Re(X conj Y), Im(X conj Y)] (functions.py:138-142).  All lanes
+// of a warp must call this together.
+BBT_DEV cf detect_pair(cf mine, bool second, int d) {
+  cf other;
+  other.x = shfl_xor(mine.x, d);
+  other.y = shfl_xor(mine.y, d);
+  cf r;
+  if (second) {   // X = other, Y = mine
+    r.x = other.x * mine.x + other.y * mine.y;
+    r.y = other.y * mine.x - other.x * mine.y;
+  } else {
+    r.x = mine.x * mine.x + mine.y * mine.y;
+    r.y = other.x * other.x + other.y * other.y;
+  }
+  return r;
+}
+
 // Pass 3: inverse column FFTs, work -> valid part of the output stream.
 template <class C>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
@@ -231,7 +256,21 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (valid) col_twiddle<C, 0>(v, a.big, (int)((unsigned)col / (unsigned)a.S), t, a.scale);
   SmemLaneFast<C::PADSHIFT> sm{smem, g, C::G};
   block_fft<C>(v, t, a.tw1, sm);
-  if (valid) {
+  if (a.detect) {
+    // Power fused in (see DdArgs::detect): columns 2q, 2q+1 -- neighbouring
+    // lanes -- are the two polarizations of a sample.
+    long long flat = (long long)t * n2s + col;
+    const long long fstep = (long long)C::T * n2s;
+    cf* dst = a.out + frame * a.out_frame_stride - a.out_shift + flat;
+    const bool second = (col & 1) != 0;
+#pragma unroll
+    for (int e = 0; e < C::E; ++e) {
+      const cf r = detect_pair(cconj(v[e]), second, 1);
+      if (valid && flat >= a.lo && flat < a.hi) *dst = r;
+      flat += fstep;
+      dst += fstep;
+    }
+  } else if (valid) {
     long long flat = (long long)t * n2s + col;
     const long long fstep = (long long)C::T * n2s;
     cf* dst = a.out + frame * a.out_frame_stride - a.out_shift + flat;
@@ -1069,7 +1108,9 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     block_fft_head<C>(v, t, a.tw1, sm);
     if (tid == 0 && next < n_tiles) issue(next);
     block_fft_tail<C>(v, t, a.tw1, sm);
-    if (!valid) continue;
+    // (With the products fused in, every lane takes part in the exchange
+    // between the lanes of a polarization pair.)
+    if (!valid && !(INVERSE && a.detect)) continue;
     if (!INVERSE) {
       twiddle(1.f);
       cf* dst = a.work + (long long)frame * a.N * a.S;
@@ -1094,11 +1135,26 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       const long long fstep = (long long)C::T * n2s;
       cf* dst = a.out + (long long)frame * a.out_frame_stride - a.out_shift +
                 flat;
+      if (a.detect) {
+        // The partner lane holds the other polarization of this sample: the
+        // first lane of a pair stores the two powers, the second the cross
+        // terms, each in the 8 bytes its voltage would have gone to.
+        const int d = planar_src ? m.tn : 1;
+        const bool second = (sser & 1u) != 0;
 #pragma unroll
-      for (int e = 0; e < C::E; ++e) {
-        if (flat >= a.lo && flat < a.hi) *dst = cconj(v[e]);
-        flat += fstep;
-        dst += fstep;
+        for (int e = 0; e < C::E; ++e) {
+          const cf r = detect_pair(cconj(v[e]), second, d);
+          if (valid && flat >= a.lo && flat < a.hi) *dst = r;
+          flat += fstep;
+          dst += fstep;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) {
+          if (flat >= a.lo && flat < a.hi) *dst = cconj(v[e]);
+          flat += fstep;
+          dst += fstep;
+        }
       }
     }
   }

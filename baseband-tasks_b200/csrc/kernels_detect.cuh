@@ -986,7 +986,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) pfb_kernel(PfbArgs a) {
 // lane are consecutive (SmemLaneSlow), so a warp reads 32 adjacent sample
 // pairs and stores 32 adjacent channels of both columns (512 bytes).
 template <class C, int KIND>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS,
+                                  (C::THREADS <= 512 ? 512 / C::THREADS : 1))
     pfb_pair_kernel(PfbArgs a) {
   static_assert(KIND == 1 || KIND == 2, "real input");
   cf* smem = BBT_SMEM(cf);

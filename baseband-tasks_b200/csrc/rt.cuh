@@ -67,14 +67,15 @@ inline unsigned atomic_add(unsigned* p, unsigned v) {
 float* bbt_emu_scratch();
 namespace bbt {
 // Exchange with the neighbouring thread (lane ^ 1), as __shfl_xor_sync does.
-inline float shfl_xor1(float v) {
+inline float shfl_xor(float v, int d) {
   float* s = bbt_emu_scratch();
   s[threadIdx.x] = v;
   bbt_emu_syncthreads();
-  const float r = s[threadIdx.x ^ 1];
+  const float r = s[threadIdx.x ^ d];
   bbt_emu_syncthreads();
   return r;
 }
+inline float shfl_xor1(float v) { return shfl_xor(v, 1); }
 inline void sincospi_d(double x, double* s, double* c) {
   *s = sin(M_PI * x);
   *c = cos(M_PI * x);
@@ -143,6 +144,9 @@ __device__ __forceinline__ unsigned atomic_add(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void sincospi_d(double x, double* s, double* c) {
   sincospi(x, s, c);
+}
+__device__ __forceinline__ float shfl_xor(float v, int d) {
+  return __shfl_xor_sync(0xffffffffu, v, d);
 }
 __device__ __forceinline__ float shfl_xor1(float v) {
   return __shfl_xor_sync(0xffffffffu, v, 1);

@@ -136,6 +136,49 @@ class Disperse(PaddedTaskBase):
         self._generic = bool(n & (n - 1))
         self._generic_parts = None
 
+    # ------------------------------------------------- Power fused in
+    # While set, frames come out of the last pass as the four products of
+    # each polarization pair (float32, in the bytes of the two voltages):
+    # `functions.Power` reads its input this way when `can_detect` says the
+    # plan has that path, and the voltages never go to memory.
+    _detect = False
+
+    def can_detect(self):
+        """Whether Power can be fused into the last dedispersion pass: the
+        polarization pair has to be the last axis of a sample."""
+        if (self._generic or self._real or len(self.sample_shape) == 0
+                or self.sample_shape[-1] != 2
+                or np.dtype(self.dtype) != np.complex64):
+            return False
+        lib = _cabi.lib()
+        return bool(lib.bbt_dedisperse_power_supported(self._get_plan()))
+
+    def read_detected(self, start, count, out=None):
+        """Samples [start, start+count) with Power applied, as a device
+        tensor of shape (count,) + sample_shape[:-1] + (4,), float32
+        (written straight into ``out`` if that is given)."""
+        single = B.torch_dtype(np.float32)
+        target = None
+        if (out is not None and out.is_contiguous() and out.dtype == single):
+            target = out.view(B.torch_dtype(np.complex64))
+        self._detect = True
+        self._frame_index = None        # cached frames hold voltages
+        try:
+            self.seek(start)
+            count = self._check_read(count, None)
+            data = B.as_device(self._read_data(count, target))
+        finally:
+            self._detect = False
+            self._frame_index = None
+        if target is not None:
+            return out
+        data = data.contiguous().view(single).reshape(
+            (count,) + self.sample_shape[:-1] + (4,))
+        if out is not None:
+            out.copy_(data)
+            return out
+        return data
+
     # ------------------------------------------------------------- the plan
     def _get_plan(self):
         if self._plan is None:
@@ -263,9 +306,10 @@ class Disperse(PaddedTaskBase):
         if self._work is None or self._work.numel() < wb:
             self._work = None
             self._work = B.empty((max(wb, 16),), np.uint8)
-        lib.check(lib.bbt_dedisperse_exec(
-            plan, B.ptr(x), spf * S, n_frames, 0, B.ptr(result), spf * S,
-            B.ptr(self._work), _cabi.stream_ptr()))
+        run = (lib.bbt_dedisperse_power_exec if self._detect
+               else lib.bbt_dedisperse_exec)
+        lib.check(run(plan, B.ptr(x), spf * S, n_frames, 0, B.ptr(result),
+                      spf * S, B.ptr(self._work), _cabi.stream_ptr()))
         if out is not None and not direct:
             out.copy_(result)
             return out

@@ -105,6 +105,22 @@ int bbt_dedisperse_exec(const bbt_dedisperse_plan* plan, const void* in,
                         int64_t in_frame_stride, int64_t n_frames,
                         int64_t skip, void* out, int64_t out_frame_stride,
                         void* work, void* stream);
+/* The same with Power (functions.py:138-142) fused into the last pass, for
+ * streams whose series come in polarization pairs (series 2q, 2q+1 = X, Y of
+ * one channel, i.e. the polarization axis is the last one): instead of the
+ * voltages X, Y the 16 bytes of a pair hold the four float32 products
+ * [|X|^2, |Y|^2, Re(X conj Y), Im(X conj Y)].  `out` is thus the
+ * (time, ..., 4) float32 output of Power(Dedisperse(...)) and the voltages
+ * never go to memory.  bbt_dedisperse_power_supported tells (1 / 0) whether
+ * the plan has this path (three-pass plans with an even number of series);
+ * bbt_dedisperse_power_exec returns BBT_EUNSUPPORTED otherwise and the
+ * caller runs bbt_dedisperse_exec and bbt_power_exec instead. */
+int bbt_dedisperse_power_supported(const bbt_dedisperse_plan* plan);
+int bbt_dedisperse_power_exec(const bbt_dedisperse_plan* plan, const void* in,
+                              int64_t in_frame_stride, int64_t n_frames,
+                              int64_t skip, void* out,
+                              int64_t out_frame_stride, void* work,
+                              void* stream);
 int bbt_dedisperse_plan_destroy(bbt_dedisperse_plan* plan);
 
 /* ---- Detection: replaces Power.task (functions.py:132-143) on (A, 2, B)

@@ -341,3 +341,38 @@ def test_c4_time_block_sharding(bt):
         np.testing.assert_array_equal(total_c.cpu().numpy(),
                                       rc.cpu().numpy())
         assert_power(total_s.cpu().numpy(), rs.cpu().numpy())
+
+
+def test_c4_power_fused_planar(bt):
+    """Power straight after the 2^24-point dedispersion of configs[3] (planar
+    work buffer: the polarizations of a pair are eight lanes apart in the last
+    pass) equals Power of the dedispersed voltages."""
+    rate, freq, dm, N = 512e6, 8192e6, 1000., 1 << 24
+    spf = N - 1889551 - 2075345
+    n = spf + N + 12345
+    g = np.random.default_rng(778)
+    x = np.empty((n, 2), np.complex64)
+    xv = x.view(np.float32)
+    for i in range(0, n, 1 << 22):
+        xv[i:i + (1 << 22)] = g.standard_normal(xv[i:i + (1 << 22)].shape,
+                                                dtype=np.float32)
+    kw = dict(frequency=freq, sideband=1, polarization=np.array(['X', 'Y']))
+    dev = bt._buffers.as_device(x)
+
+    def chain():
+        src = bt.ArrayStream(dev, t0(bt), rate, samples_per_frame=1 << 20,
+                             **kw)
+        return bt.Dedisperse(src, dm, samples_per_frame=spf)
+
+    fused = bt.Power(chain())
+    assert fused._fused
+    dd = chain()
+    for start, count in ((0, 2 * spf), (spf - 1000, 5000),
+                         (2 * spf, fused.shape[0] - 2 * spf)):
+        dd.seek(start)
+        v = dd.read(count)
+        want = orc.power(v.astype(np.complex128), axis=1)
+        fused.seek(start)
+        got = fused.read(count)
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert_power(got, want)

@@ -951,3 +951,45 @@ def test_integrate_long_channelizer_unfused(bt):
     want, count = orc.integrate(power, np.array([0, 3]))
     assert np.all(got['count'] == 3)
     assert_power(got['data'], want)
+
+
+@pytest.mark.parametrize('shape', [(2,), (3, 2), (9, 2)])
+def test_power_fused_into_dedispersion(bt, shape):
+    """Power straight after Dedisperse is formed by the last dedispersion
+    pass (bbt_dedisperse_power_exec): same numbers as the two tasks apart
+    (functions.py:138-142 after dispersion.py:135-139), for whole reads,
+    reads across frame boundaries and the partial last frame."""
+    rate, dm = 1e6, 2.
+    n_chan = int(np.prod(shape[:-1], dtype=int))
+    freq = (300e6 + 1e6 * np.arange(n_chan)).reshape(shape[:-1] + (1,))
+    n = 3 * 32768 + 5000
+    x = cnoise(np.random.default_rng(5), (n,) + shape)
+    kw = dict(frequency=freq if n_chan > 1 else 300e6, sideband=1,
+              polarization=np.array(['X', 'Y']))
+    src = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=4096, **kw)
+    dd = bt.Dedisperse(src, dm, samples_per_frame=32768 - 1000)
+    fused = bt.Power(dd)
+    assert fused._fused
+    src2 = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=4096, **kw)
+    dd2 = bt.Dedisperse(src2, dm, samples_per_frame=32768 - 1000)
+    v = dd2.read()
+    want = orc.power(v.astype(np.complex128), axis=v.ndim - 1)
+    assert fused.shape == want.shape
+    got = fused.read()
+    assert got.dtype == np.float32
+    assert_power(got, want)
+    fused.seek(31000)
+    assert_power(fused.read(2000), want[31000:33000])
+    # The voltages are still what they were.
+    dd.seek(100)
+    assert_voltage(dd.read(50), v[100:150])
+    # A read that goes in several blocks (products written straight into
+    # slices of the result).
+    from baseband_tasks_b200 import base
+    saved = base.BLOCK_BYTES
+    base.BLOCK_BYTES = 40000 * 16 * (fused.shape[1] if fused.ndim > 2 else 1)
+    try:
+        fused.seek(0)
+        assert_power(fused.read(), want)
+    finally:
+        base.BLOCK_BYTES = saved
