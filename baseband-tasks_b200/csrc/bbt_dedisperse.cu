@@ -100,7 +100,15 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
   const int per_sm = C::THREADS <= 256 ? 2 : 1;
   const int64_t ctas = std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
   int rc;
-  if (inverse) {
+  if (inverse && a.detect) {
+    auto kern = dd_col_tma_kernel<C, true, true>;
+    if (BBT_SET_SMEM(kern, smem))
+      return fail(BBT_ECUDA, "cannot set shared memory size");
+    prof_next_name = "dd_col_inv";
+    BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a, m,
+               map);
+    rc = check_launch("dedispersion column kernel");
+  } else if (inverse) {
     auto kern = dd_col_tma_kernel<C, true>;
     if (BBT_SET_SMEM(kern, smem))
       return fail(BBT_ECUDA, "cannot set shared memory size");
@@ -293,7 +301,8 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
   p->half = (hint >> 12) & 3;  // bit 0: column passes, bit 1: row pass
   const int hint_l1 = hint & 0xff;
   const bool force_planar = (hint >> 8) & 1, force_inter = (hint >> 9) & 1;
-  if (l <= kLog2TwiddleTable && (n_series == 1 || l <= 10) && !hint_l1) {
+  if (l <= kLog2TwiddleTable &&
+      (n_series == 1 || l <= tune("dd_small_max", 10)) && !hint_l1) {
     p->log2n1 = 0;  // single pass
     p->log2n2 = l;
   } else {
@@ -565,7 +574,7 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.n_frames = (int)n_frames;
   int rc = BBT_EUNSUPPORTED;
   if (p->log2n1 == 0) {
-    const bool lanefast = p->n_series > 1;
+    const bool lanefast = p->n_series > 1 && tune("dd_small_lanefast", 1);
 #define F(L)                                                        \
   rc = lanefast ? launch_dd_small<L, true>(a, n_frames, st)         \
                 : launch_dd_small<L, false>(a, n_frames, st)

@@ -974,9 +974,10 @@ struct DdColTma {
                     // other exchanges and stores)
 };
 
-template <class C, bool INVERSE>
+template <class C, bool INVERSE, bool DETECT = false>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     dd_col_tma_kernel(DdArgs a, DdColTma m, BBT_TMAP_PARAM map) {
+  static_assert(INVERSE || !DETECT, "products are formed by the last pass");
   cf* smem = BBT_SMEM(cf);
   // The barrier sits behind the exchange buffer (or the landing zone, for
   // transforms without an exchange).
@@ -1110,7 +1111,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     block_fft_tail<C>(v, t, a.tw1, sm);
     // (With the products fused in, every lane takes part in the exchange
     // between the lanes of a polarization pair.)
-    if (!valid && !(INVERSE && a.detect)) continue;
+    if (!valid && !DETECT) continue;
     if (!INVERSE) {
       twiddle(1.f);
       cf* dst = a.work + (long long)frame * a.N * a.S;
@@ -1135,7 +1136,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
       const long long fstep = (long long)C::T * n2s;
       cf* dst = a.out + (long long)frame * a.out_frame_stride - a.out_shift +
                 flat;
-      if (a.detect) {
+      if constexpr (DETECT) {
         // The partner lane holds the other polarization of this sample: the
         // first lane of a pair stores the two powers, the second the cross
         // terms, each in the 8 bytes its voltage would have gone to.
@@ -1164,7 +1165,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
 // LANEFAST (S > 1): consecutive threads take consecutive series; otherwise
 // consecutive threads walk along time.
 template <class C, bool LANEFAST>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     dd_small_kernel(DdArgs a, long long n_frames) {
   cf* smem = BBT_SMEM(cf);
   const int tid = threadIdx.x;

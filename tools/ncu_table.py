@@ -1,5 +1,5 @@
 """Markdown table of the per-kernel metrics quoted in profiles/*.md from an
-ncu report (`ncu --set full`): python tools/ncu_table.py report.ncu-rep [regex]"""
+ncu report (`ncu --set full`): python tools/ncu_table.py report.ncu-rep|raw.csv [regex]"""
 import csv
 import io
 import re
@@ -34,8 +34,12 @@ STALL_NAMES = ['long_scoreboard', 'math_pipe_throttle', 'not_selected', 'barrier
 def main():
     rep = sys.argv[1]
     pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'],
-                         capture_output=True, text=True, check=True).stdout
+    if rep.endswith('.csv'):      # already exported with --page raw --csv
+        out = open(rep).read()
+        out = out[out.index('"ID"'):]
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'],
+                             capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
