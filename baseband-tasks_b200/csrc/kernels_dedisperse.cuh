@@ -355,8 +355,21 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
         // DRAM sees whole lines rather than the 64-byte pieces of one tile.
         const unsigned chunks = a.row_chunks;
         const unsigned rb = nb / chunks, ck = nb - rb * chunks;
-        elems = (long long)a.row_rpc * C::N * a.S / chunks;
-        base2 += ((long long)rb * a.row_rpc) * C::N * a.S + ck * elems;
+        if (chunks > 4) {
+          // Many series (C3: 2050, 257 tiles per row block of 17 MB): the
+          // CTAs of a row block are too far apart in time for shares
+          // fetched by one to still be in L2 when the others come for them
+          // (measured: 2.6 x the data read from DRAM).  Each tile's own
+          // runs, then: rpc * N of them, S elements apart.
+          prefetch_tile(base2 + ((long long)rb * a.row_rpc) * C::N * a.S +
+                            (long long)ck * a.row_sc,
+                        (int)a.row_rpc * C::N, a.S, (int)a.row_sc, tid,
+                        C::THREADS);
+          elems = 0;
+        } else {
+          elems = (long long)a.row_rpc * C::N * a.S / chunks;
+          base2 += ((long long)rb * a.row_rpc) * C::N * a.S + ck * elems;
+        }
       }
       const long long limit = a.N * a.S - (base2 - (a.work + nf * a.N * a.S));
       if (elems > limit) elems = limit;
