@@ -278,7 +278,14 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) chanpow_kernel(ChanPowArgs a) {
 // jl so that what a half-warp reads falls in distinct banks.
 template <class C>
 struct ChanPowTma {
-  static constexpr int kStages = 2;
+#ifndef BBT_CHANPOW_STAGES
+// One stage: the copy of the next tile is issued as soon as every thread has
+// taken its values of this one and lands during the transform; a second stage
+// bought nothing and its 33 KB cost 13 % (C4, 4 lanes: 1.53 -> 1.34 ms per 32
+// frames), with a register cap for three CTAs per SM on top 1.53 again.
+#define BBT_CHANPOW_STAGES 1
+#endif
+  static constexpr int kStages = BBT_CHANPOW_STAGES;
   static BBT_HD constexpr long long spectrum_elems(long long M) {
     return (long long)C::N * M * 2;
   }
@@ -303,8 +310,12 @@ struct ChanPowTma {
   }
 };
 
+#ifndef BBT_CHANPOW_CTAS
+#define BBT_CHANPOW_CTAS 1
+#endif
 template <class C>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1)
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS,
+                                  (C::THREADS <= 128 ? BBT_CHANPOW_CTAS : 1))
     chanpow_tma_kernel(ChanPowArgs a) {
   static_assert(C::G % 2 == 0 && C::E % 2 == 0, "pairs of lanes and values");
   using K = ChanPowTma<C>;
