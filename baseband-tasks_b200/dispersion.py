@@ -150,8 +150,13 @@ class Disperse(PaddedTaskBase):
                 or self.sample_shape[-1] != 2
                 or np.dtype(self.dtype) != np.complex64):
             return False
-        lib = _cabi.lib()
-        return bool(lib.bbt_dedisperse_power_supported(self._get_plan()))
+        try:
+            lib = _cabi.lib()
+            return bool(lib.bbt_dedisperse_power_supported(self._get_plan()))
+        except _cabi.BBTError:
+            # No plan for this frame length (or no device yet): the tasks
+            # run one after the other and report the problem when read.
+            return False
 
     def read_detected(self, start, count, out=None):
         """Samples [start, start+count) with Power applied, as a device
