@@ -72,6 +72,10 @@ _SIGNATURES = {
     'bbt_shift_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                c_int, c_void_p]),
     'bbt_convert_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'bbt_pair_frames_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int64,
+                                     c_int64, c_int64, c_int64, c_void_p]),
+    'bbt_unpair_frames_exec': (c_int, [c_void_p, c_void_p, c_int64, c_int64,
+                                       c_int64, c_void_p]),
     'bbt_decode_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                 c_void_p]),
     'bbt_average_exec': (c_int, [c_void_p, c_void_p, c_void_p, c_int64,

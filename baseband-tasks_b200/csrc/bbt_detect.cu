@@ -412,6 +412,39 @@ int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
   return check_launch("conversion kernel");
 }
 
+int bbt_pair_frames_exec(const void* in, void* out, int64_t n_in,
+                         int64_t samples_per_frame, int64_t n, int64_t n_series,
+                         int64_t n_frames, void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (n_in <= 0 || samples_per_frame <= 0 || n < samples_per_frame ||
+      n_series <= 0)
+    return fail(BBT_EINVAL, "bad frame shape");
+  if (n_frames <= 0) return BBT_OK;
+  const int64_t n_pairs = (n_frames + 1) / 2;
+  BBT_LAUNCH(pair_frames_kernel, dim3(grid_for(n_pairs * n * n_series, 256)),
+             dim3(256), 0, as_stream(stream), static_cast<const float*>(in),
+             static_cast<cf*>(out), (long long)n_in,
+             (long long)samples_per_frame, (long long)n, (long long)n_series,
+             (long long)n_pairs);
+  return check_launch("frame pairing kernel");
+}
+
+int bbt_unpair_frames_exec(const void* in, void* out,
+                           int64_t samples_per_frame, int64_t n_series,
+                           int64_t n_frames, void* stream) {
+  if (!in || !out) return fail(BBT_EINVAL, "null argument");
+  if (samples_per_frame <= 0 || n_series <= 0)
+    return fail(BBT_EINVAL, "bad frame shape");
+  if (n_frames <= 0) return BBT_OK;
+  const int64_t n_pairs = (n_frames + 1) / 2;
+  BBT_LAUNCH(unpair_frames_kernel,
+             dim3(grid_for(n_pairs * samples_per_frame * n_series, 256)),
+             dim3(256), 0, as_stream(stream), static_cast<const cf*>(in),
+             static_cast<float*>(out), (long long)samples_per_frame,
+             (long long)n_series, (long long)n_frames);
+  return check_launch("frame unpairing kernel");
+}
+
 int bbt_decode_exec(const void* in, void* out, const float* levels, int64_t n,
                     int bps, void* stream) {
   if (!in || !out || !levels) return fail(BBT_EINVAL, "null argument");

@@ -1171,6 +1171,41 @@ BBT_GLOBAL void complex_to_real_kernel(const cf* BBT_RESTRICT in,
     out[i] = in[i].x;
 }
 
+// Two real overlap-save frames as one complex frame: a real response (the
+// Hermitian phase factor of a real-valued stream, i.e. rfft -> x factor ->
+// irfft) convolves the real and the imaginary part separately, so frames 2p
+// and 2p+1 of a real stream ride through the complex kernels together and
+// come out as the real and imaginary part of the result.
+//   pack:   z[p][n][s] = x[(2p) spf + n][s] + i x[(2p+1) spf + n][s], n < N
+//           (zero where the stream of n_in samples has ended)
+//   unpack: y[(2p) spf + m][s] = Re w[p][m][s], y[(2p+1) spf + m][s] = Im,
+//           m < spf, for the n_frames frames that exist.
+BBT_GLOBAL void pair_frames_kernel(const float* BBT_RESTRICT in,
+                                   cf* BBT_RESTRICT out, long long n_in,
+                                   long long spf, long long N, long long S,
+                                   long long n_pairs) {
+  const long long per = N * S, total = n_pairs * per, limit = n_in * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+       i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / per, r = i - p * per;
+    const long long a = (2 * p) * spf * S + r, b = a + spf * S;
+    out[i] = mk(a < limit ? in[a] : 0.f, b < limit ? in[b] : 0.f);
+  }
+}
+BBT_GLOBAL void unpair_frames_kernel(const cf* BBT_RESTRICT in,
+                                     float* BBT_RESTRICT out, long long spf,
+                                     long long S, long long n_frames) {
+  const long long per = spf * S, n_pairs = (n_frames + 1) / 2;
+  const long long total = n_pairs * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+       i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / per, r = i - p * per;
+    const cf w = in[i];
+    out[(2 * p) * per + r] = w.x;
+    if (2 * p + 1 < n_frames) out[(2 * p + 1) * per + r] = w.y;
+  }
+}
+
 // Packed payload decode: value v occupies bits [v*bps, (v+1)*bps) of the byte
 // stream (first value in the least significant bits) and maps to levels[code].
 // One thread per four output values, so stores are full float4 lines.

@@ -376,19 +376,38 @@ class Disperse(PaddedTaskBase):
         return table[self._series_map].T.reshape((n,) + self.ih.sample_shape)
 
     def _task_frames_real(self, data, n_frames, out, host):
+        """Real-valued streams: frames 2p and 2p+1 go through the complex
+        kernels as the real and imaginary part of one frame (the Hermitian
+        response is a real convolution, which treats the two separately)."""
         lib = _cabi.lib()
+        plan = self._get_plan()
         x = B.as_device(data, dtype=np.float32)
-        xc = B.empty(x.shape, np.complex64)
-        lib.check(lib.bbt_convert_exec(B.ptr(x), B.ptr(xc), x.numel(), 0,
-                                       _cabi.stream_ptr()))
-        yc = self._exec_frames(xc, n_frames, None)
-        result = out
-        if result is None or result.dtype != B.torch_dtype(np.float32):
-            result = B.empty(yc.shape, np.float32)
-        lib.check(lib.bbt_convert_exec(B.ptr(yc), B.ptr(result), yc.numel(),
-                                       1, _cabi.stream_ptr()))
+        S, spf = self._n_series, self.samples_per_frame
+        N = self._ih_samples_per_frame
+        assert x.shape[0] == (n_frames - 1) * spf + N
+        n_pairs = (n_frames + 1) // 2
+        z = B.empty((n_pairs * N,) + self.sample_shape, np.complex64)
+        lib.check(lib.bbt_pair_frames_exec(B.ptr(x), B.ptr(z), x.shape[0],
+                                           spf, N, S, n_frames,
+                                           _cabi.stream_ptr()))
+        w = B.empty((n_pairs * spf,) + self.sample_shape, np.complex64)
+        wb = lib.bbt_dedisperse_work_bytes(plan, n_pairs)
+        if self._work is None or self._work.numel() < wb:
+            self._work = None
+            self._work = B.empty((max(wb, 16),), np.uint8)
+        lib.check(lib.bbt_dedisperse_exec(
+            plan, B.ptr(z), N * S, n_pairs, 0, B.ptr(w), spf * S,
+            B.ptr(self._work), _cabi.stream_ptr()))
+        del z
+        single = B.torch_dtype(np.float32)
+        direct = (out is not None and out.is_contiguous()
+                  and out.dtype == single)
+        result = out if direct else B.empty(
+            (n_frames * spf,) + self.sample_shape, np.float32)
+        lib.check(lib.bbt_unpair_frames_exec(B.ptr(w), B.ptr(result), spf, S,
+                                             n_frames, _cabi.stream_ptr()))
         if out is not None:
-            if result is not out:
+            if not direct:
                 out.copy_(result)
             return out
         if self.dtype != np.dtype(np.float32):

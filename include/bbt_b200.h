@@ -207,6 +207,25 @@ int bbt_shift_exec(const void* in, void* out, const int64_t* offset,
  * Hermitian response. */
 int bbt_convert_exec(const void* in, void* out, int64_t n, int to_real,
                      void* stream);
+/* Real-valued streams, two overlap-save frames per complex frame.  The
+ * response of a real stream (rfft -> x phase factor -> irfft,
+ * dispersion.py:115-139 with fourier/numpy.py:41-49) is a real convolution,
+ * which acts on the real and the imaginary part of a complex series
+ * separately; so frames 2p and 2p+1 (each n samples, samples_per_frame
+ * apart, in a run of n_in real samples x n_series) are packed as
+ * z[p] = x[2p] + i x[2p+1] into `out` ([(n_frames+1)/2][n][n_series]
+ * complex64, zero beyond the end of the run), go through
+ * bbt_dedisperse_exec as (n_frames+1)/2 frames with in_frame_stride =
+ * n * n_series, and bbt_unpair_frames_exec writes the real and imaginary
+ * parts of the [(n_frames+1)/2][samples_per_frame][n_series] result back as
+ * the n_frames * samples_per_frame real output samples: half the transforms
+ * and half the traffic of one complex frame per real frame. */
+int bbt_pair_frames_exec(const void* in, void* out, int64_t n_in,
+                         int64_t samples_per_frame, int64_t n, int64_t n_series,
+                         int64_t n_frames, void* stream);
+int bbt_unpair_frames_exec(const void* in, void* out,
+                           int64_t samples_per_frame, int64_t n_series,
+                           int64_t n_frames, void* stream);
 
 /* ---- Packed payload decode (the VDIF-style encodings of baseband, which the
  * reference's coded HDF5 payloads reuse, io/hdf5/payload.py:165-166): value v
