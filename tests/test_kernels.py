@@ -348,6 +348,73 @@ def test_dedisperse_set_response(backend):
         dd.close()
 
 
+@pytest.mark.parametrize('n_frames,S', [(1, 1), (4, 2), (5, 3)])
+def test_real_frames_in_pairs(backend, n_frames, S):
+    """A real-valued stream through the complex plan two frames at a time
+    (bbt_pair_frames_exec / bbt_unpair_frames_exec): with a real response --
+    the Hermitian extension of the rfft phase factor -- the real and imaginary
+    parts of a complex frame are convolved separately, so each real frame
+    comes out as irfft(rfft(x) * factor) (dispersion.py:135-139 with
+    fourier/numpy.py:41-49).  Odd frame counts leave the last imaginary part
+    empty."""
+    b, lib = backend, backend.lib
+    rng = np.random.default_rng(100 * n_frames + S)
+    N, pad_start, spf = 2048, 100, 2048 - 300
+    n_in = (n_frames - 1) * spf + N
+    x = rng.standard_normal((n_in, S)).astype('f4')
+    half = np.exp(2j * np.pi * rng.uniform(size=(1, N // 2 + 1)))
+    half[0, 0] = 1.
+    half[0, -1] = -1.
+    full = np.empty((1, N), 'c8')
+    full[:, :N // 2 + 1] = half
+    full[:, N // 2 + 1:] = half[:, N // 2 - 1:0:-1].conj()
+    smap = np.zeros(S, np.int32)
+    one = np.array([300.])
+    plan = ctypes.c_void_p()
+    dbl = ctypes.POINTER(ctypes.c_double)
+    lib.check(lib.bbt_dedisperse_plan_create(
+        ctypes.byref(plan), N, S, pad_start, spf, 1,
+        smap.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+        one.ctypes.data_as(dbl), one.ctypes.data_as(dbl),
+        np.array([1], np.int8).ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+        1., 1., 0., 0))
+    try:
+        lib.check(lib.bbt_dedisperse_plan_set_response(
+            plan, full.ctypes.data_as(ctypes.c_void_p)))
+        n_pairs = (n_frames + 1) // 2
+        d_in = b.to_dev(x)
+        z = b.empty((n_pairs * N, S), 'c8')
+        lib.check(lib.bbt_pair_frames_exec(b.ptr(d_in), b.ptr(z), n_in, spf,
+                                           N, S, n_frames, b.stream))
+        b.sync()
+        zh = b.to_host(z).reshape(n_pairs, N, S)
+        for p in range(n_pairs):
+            np.testing.assert_array_equal(
+                zh[p].real, x[2 * p * spf:2 * p * spf + N])
+            second = np.zeros((N, S), 'f4')
+            if 2 * p + 1 < n_frames:
+                second = x[(2 * p + 1) * spf:(2 * p + 1) * spf + N]
+            np.testing.assert_array_equal(zh[p].imag, second)
+        w = b.empty((n_pairs * spf, S), 'c8')
+        wb = lib.bbt_dedisperse_work_bytes(plan, n_pairs)
+        work = b.empty((max(wb, 8) // 8,), 'c8')
+        lib.check(lib.bbt_dedisperse_exec(plan, b.ptr(z), N * S, n_pairs, 0,
+                                          b.ptr(w), spf * S, b.ptr(work),
+                                          b.stream))
+        y = b.zeros((n_frames * spf, S), 'f4')
+        lib.check(lib.bbt_unpair_frames_exec(b.ptr(w), b.ptr(y), spf, S,
+                                             n_frames, b.stream))
+        b.sync()
+        got = b.to_host(y)
+        for f in range(n_frames):
+            frame = x[f * spf:f * spf + N].astype('f8')
+            want = np.fft.irfft(np.fft.rfft(frame, axis=0) * half[0][:, None],
+                                n=N, axis=0)[pad_start:pad_start + spf]
+            assert_voltage(got[f * spf:(f + 1) * spf], want)
+    finally:
+        lib.bbt_dedisperse_plan_destroy(plan)
+
+
 # ---------------------------------------------------------------- detection
 @pytest.mark.parametrize('a,b', [(1000, 1), (37, 5), (1, 300)])
 def test_power(backend, a, b):
