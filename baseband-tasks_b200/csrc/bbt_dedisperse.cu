@@ -182,7 +182,12 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
         return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
       const size_t smem = Row2Cfg<C>::kSmemBytes;
       const bool regen = a.ch_freq && tune("chirp_regen", 0);
-      auto kern = regen ? dd_row2_kernel<C, true> : dd_row2_kernel<C, false>;
+      // Pieces of >= 2 KB landing at the pitch of the exchange matrix.
+      constexpr bool kCanLandP = L2 >= 13;
+      const bool landp = kCanLandP && !regen && tune("row_landp", 0);
+      auto kern = regen ? dd_row2_kernel<C, true>
+                        : (landp ? dd_row2_kernel<C, false, kCanLandP>
+                                 : dd_row2_kernel<C, false>);
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
       const int64_t ctas =

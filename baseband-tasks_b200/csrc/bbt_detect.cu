@@ -425,7 +425,7 @@ int bbt_pair_frames_exec(const void* in, void* out, int64_t n_in,
              dim3(256), 0, as_stream(stream), static_cast<const float*>(in),
              static_cast<cf*>(out), (long long)n_in,
              (long long)samples_per_frame, (long long)n, (long long)n_series,
-             (long long)n_pairs);
+             (long long)n_frames);
   return check_launch("frame pairing kernel");
 }
 

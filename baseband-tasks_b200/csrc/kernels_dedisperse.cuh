@@ -500,10 +500,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
     const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
     const unsigned bytes = tile_bytes(rho0);
     mbar_expect_tx(bar, bytes);
-    char* dst = reinterpret_cast<char*>(smem);
-    for (unsigned o = 0; o < bytes; o += kChunk)
-      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
-                o + kChunk >= bytes);
+    row2_load<C, LANDP>(smem, src, bytes, bar);
   }
   unsigned k = 0;
 #pragma unroll 1
@@ -752,7 +749,31 @@ BBT_DEV void stagger_out(int grp, int n_grp, int flags) {
   if ((flags & 1) && grp + 1 < n_grp) named_bar_arrive(grp + 1, 256);
 }
 
-template <class C, bool REGEN>
+// The copies that bring a tile of rows into shared memory.  LANDP: every
+// M-point piece x[M e .. M e + M) of a row lands at the pitch P of the
+// exchange matrix X, so that the thread which takes x[u + M e] out of the
+// landing zone later writes its butterflies' results to the very same places
+// (X[e P + u]) and no barrier is needed between the two; otherwise the tile
+// lands as it lies in memory, in chunks of 32 KB.
+template <class C, bool LANDP>
+BBT_DEV void row2_load(cf* smem, const char* src, unsigned bytes, Mbar* bar) {
+  char* dst = reinterpret_cast<char*>(smem);
+  if constexpr (LANDP) {
+    constexpr unsigned kPiece = Row2Cfg<C>::M * sizeof(cf);
+    constexpr unsigned kPitch = Row2Cfg<C>::P * sizeof(cf);
+    const unsigned n = bytes / kPiece;
+    for (unsigned i = 0; i < n; ++i)
+      bulk_load(dst + (size_t)i * kPitch, src + (size_t)i * kPiece, kPiece, bar,
+                i + 1 == n);
+  } else {
+    constexpr unsigned kChunk = 32 * 1024;
+    for (unsigned o = 0; o < bytes; o += kChunk)
+      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
+                o + kChunk >= bytes);
+  }
+}
+
+template <class C, bool REGEN, bool LANDP>
 BBT_DEV_NOINLINE void dd_row2_tile(
     cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw,
     const cf* tw_sub, bool valid, unsigned phase, const char* next_src,
@@ -770,7 +791,6 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   const int tid = threadIdx.x;
   const int u = tid % C::T, g = tid / C::T;
   const int k1 = u / Ts, tt = u % Ts;        // sub-transform and place in it
-  constexpr unsigned kChunk = 32 * 1024;
   cf* X = smem + (size_t)g * 32 * P;         // this row's [32][P] matrix
   const cf* tab_outer = reinterpret_cast<const cf*>(bar + 2);
   const cf* tab_sub = tab_outer + R::kTabOuter;
@@ -778,18 +798,20 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   cf v[32];
   stagger_in(grp, flags);
   {
-    const cf* land = smem + g * C::N + u;
+    const cf* land = LANDP ? X + u : smem + g * C::N + u;
+    constexpr int pitch = LANDP ? P : M;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = valid ? land[M * e] : mk(0.f, 0.f);
+    for (int e = 0; e < 32; ++e) v[e] = valid ? land[pitch * e] : mk(0.f, 0.f);
   }
   stagger_out(grp, kGroups, flags);
   // The landing zone becomes the exchange buffer once every thread has taken
-  // its values; the butterflies in between need registers only.
-  if (!(flags & 2)) BBT_SYNC();
+  // its values (with LANDP a thread overwrites only what it took itself); the
+  // butterflies in between need registers only.
+  if (!LANDP && !(flags & 2)) BBT_SYNC();
   // Forward: over e in this thread, twiddle, transpose.
   Dft<32>::run(v);
   apply_twiddles_tab<32>(v, tab_outer, M, u);
-  if (flags & 2) BBT_SYNC();
+  if (!LANDP && (flags & 2)) BBT_SYNC();
 #pragma unroll
   for (int r = 0; r < 32; ++r) X[r * P + u] = v[r];
   BBT_SYNC();
@@ -853,11 +875,7 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   if (tid == ((flags & 4) ? C::THREADS - 32 : 0) && next_bytes) {
     fence_proxy_async();
     mbar_expect_tx(bar, next_bytes);
-    char* dst = reinterpret_cast<char*>(smem);
-    for (unsigned o = 0; o < next_bytes; o += kChunk)
-      bulk_load(dst + o, next_src + o,
-                next_bytes - o < kChunk ? next_bytes - o : kChunk, bar,
-                o + kChunk >= next_bytes);
+    row2_load<C, LANDP>(smem, next_src, next_bytes, bar);
   }
   Dft<32>::run(v);
   if (valid) {
@@ -866,7 +884,7 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   }
 }
 
-template <class C, bool REGEN>
+template <class C, bool REGEN, bool LANDP = false>
 BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   Mbar* bar = reinterpret_cast<Mbar*>(smem + Row2Cfg<C>::kElems);
@@ -910,10 +928,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
     const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
     const unsigned bytes = tile_bytes(rho0);
     mbar_expect_tx(bar, bytes);
-    char* dst = reinterpret_cast<char*>(smem);
-    for (unsigned o = 0; o < bytes; o += kChunk)
-      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
-                o + kChunk >= bytes);
+    row2_load<C, LANDP>(smem, src, bytes, bar);
   }
   unsigned k = 0;
 #pragma unroll 1
@@ -950,8 +965,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
       rg.rate_mhz = a.ch_rate, rg.soff = a.ch_soff;
       rg.k1 = k1, rg.n1 = n1, rg.N = a.N, rg.log2n2 = a.log2n2;
     }
-    dd_row2_tile<C, REGEN>(smem, bar, row, chirp, a.tw, a.tw_sub, valid, k,
-                           next_src, next_bytes, &rg);
+    dd_row2_tile<C, REGEN, LANDP>(smem, bar, row, chirp, a.tw, a.tw_sub, valid,
+                                  k, next_src, next_bytes, &rg);
   }
 }
 

@@ -1183,13 +1183,15 @@ BBT_GLOBAL void complex_to_real_kernel(const cf* BBT_RESTRICT in,
 BBT_GLOBAL void pair_frames_kernel(const float* BBT_RESTRICT in,
                                    cf* BBT_RESTRICT out, long long n_in,
                                    long long spf, long long N, long long S,
-                                   long long n_pairs) {
-  const long long per = N * S, total = n_pairs * per, limit = n_in * S;
+                                   long long n_frames) {
+  const long long per = N * S, total = ((n_frames + 1) / 2) * per;
+  const long long limit = n_in * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
        i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / per, r = i - p * per;
     const long long a = (2 * p) * spf * S + r, b = a + spf * S;
-    out[i] = mk(a < limit ? in[a] : 0.f, b < limit ? in[b] : 0.f);
+    out[i] = mk(a < limit ? in[a] : 0.f,
+                2 * p + 1 < n_frames && b < limit ? in[b] : 0.f);
   }
 }
 BBT_GLOBAL void unpair_frames_kernel(const cf* BBT_RESTRICT in,
