@@ -176,22 +176,34 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   }
   if (blocks * n_frames > 2147483647LL)
     return fail(BBT_EUNSUPPORTED, "grid too large");
-  if constexpr (PLANAR && !HALF && L2 >= 11) {
+  // (HALF: rows of up to 8192 points in 256-thread CTAs, two per SM, which
+  // do not wait for one another.)
+  if constexpr (PLANAR && L2 >= 11 && (!HALF || L2 <= 13)) {
     if (a.tw_sub) {   // the plan stored its chirp for dd_row2_kernel
       if (reinterpret_cast<uintptr_t>(a.work) & 15)
         return fail(BBT_EINVAL, "work buffer must be 16-byte aligned");
-      const size_t smem = Row2Cfg<C>::kSmemBytes;
+      size_t smem = Row2Cfg<C>::kSmemBytes;
       const bool regen = a.ch_freq && tune("chirp_regen", 0);
-      // Pieces of >= 2 KB landing at the pitch of the exchange matrix.
-      constexpr bool kCanLandP = L2 >= 13;
-      const bool landp = kCanLandP && !regen && tune("row_landp", 0);
-      auto kern = regen ? dd_row2_kernel<C, true>
-                        : (landp ? dd_row2_kernel<C, false, kCanLandP>
-                                 : dd_row2_kernel<C, false>);
+      // row_landp 1: pieces of >= 2 KB landing at the pitch of the exchange
+      // matrix; 2 (one row per tile): half of the next row lands in a side
+      // buffer a whole row time ahead.
+      constexpr int kCanLandP = L2 >= 13 ? 1 : 0;
+      constexpr int kCanSide =
+          (C::G == 1 && Row2Cfg<C>::kSmemBytesSide <= 232448) ? 2 : kCanLandP;
+      const int landp = regen || !kCanLandP ? 0 : tune("row_landp", 0);
+      auto kern = dd_row2_kernel<C, false>;
+      if (regen) {
+        kern = dd_row2_kernel<C, true>;
+      } else if (landp == 2 && kCanSide == 2) {
+        kern = dd_row2_kernel<C, false, kCanSide>;
+        smem = Row2Cfg<C>::kSmemBytesSide;
+      } else if (landp) {
+        kern = dd_row2_kernel<C, false, kCanLandP>;
+      }
       if (BBT_SET_SMEM(kern, smem))
         return fail(BBT_ECUDA, "cannot set shared memory size");
-      const int64_t ctas =
-          std::min<int64_t>(blocks * n_frames, (int64_t)sm_count());
+      const int64_t ctas = std::min<int64_t>(
+          blocks * n_frames, (int64_t)sm_count() * (HALF ? 2 : 1));
       prof_next_name = "dd_row";
       BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C::THREADS), smem, st, a);
       return check_launch("dedispersion row kernel");
@@ -348,8 +360,8 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     if (!planar && !((hint >> 14) & 1) && !whole_rows) p->half |= 2;
   }
   // Long contiguous rows: the formulation with warp-local sub-transforms.
-  p->row2 = p->log2n1 > 0 && p->planar && p->log2n2 >= 11 && !(p->half & 2) &&
-            tune("row2", 1);
+  p->row2 = p->log2n1 > 0 && p->planar && p->log2n2 >= 11 &&
+            (!(p->half & 2) || p->log2n2 <= 13) && tune("row2", 1);
   p->tw_sub = p->row2 ? twiddle_table(p->log2n2 - 5) : nullptr;
   if (p->row2 && !p->tw_sub) p->row2 = 0;
   p->tw2 = twiddle_table(p->log2n2);

@@ -500,7 +500,10 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row_tma_kernel(DdArgs a) {
     const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
     const unsigned bytes = tile_bytes(rho0);
     mbar_expect_tx(bar, bytes);
-    row2_load<C, LANDP>(smem, src, bytes, bar);
+    char* dst = reinterpret_cast<char*>(smem);
+    for (unsigned o = 0; o < bytes; o += kChunk)
+      bulk_load(dst + o, src + o, bytes - o < kChunk ? bytes - o : kChunk, bar,
+                o + kChunk >= bytes);
   }
   unsigned k = 0;
 #pragma unroll 1
@@ -719,6 +722,13 @@ struct Row2Cfg {
   static constexpr size_t kSmemBytes =
       kElems * sizeof(cf) + 2 * sizeof(Mbar) +
       (kTabOuter + CS::twtab_size()) * sizeof(cf);
+  // Side buffer (dd_row2_kernel with LAND = 2, one row per tile): the first
+  // kSide of the 32 M-point pieces of the NEXT row land here while the
+  // current row is still being worked on in X.
+  static constexpr int kSide = 16;
+  static constexpr size_t kSideOffset = (kSmemBytes + 127) / 128 * 128;
+  static constexpr size_t kSmemBytesSide =
+      kSideOffset + (size_t)kSide * M * sizeof(cf);
 };
 
 struct ChirpRegen {          // per row: what chirp_value needs
@@ -755,10 +765,35 @@ BBT_DEV void stagger_out(int grp, int n_grp, int flags) {
 // landing zone later writes its butterflies' results to the very same places
 // (X[e P + u]) and no barrier is needed between the two; otherwise the tile
 // lands as it lies in memory, in chunks of 32 KB.
-template <class C, bool LANDP>
+// LAND = 2 (one row per tile): the first kSide pieces go to a side buffer --
+// issued as soon as the previous row has been taken out of it, a whole row
+// time before they are needed -- and only the rest to X once X is free.
+template <class C>
+BBT_DEV void row2_load_side(cf* smem, const char* src, Mbar* bar_side) {
+  using R = Row2Cfg<C>;
+  constexpr unsigned kPiece = R::M * sizeof(cf);
+  char* dst = reinterpret_cast<char*>(smem) + R::kSideOffset;
+  mbar_expect_tx(bar_side, R::kSide * kPiece);
+  for (unsigned i = 0; i < (unsigned)R::kSide; ++i)
+    bulk_load(dst + (size_t)i * kPiece, src + (size_t)i * kPiece, kPiece,
+              bar_side, i + 1 == (unsigned)R::kSide);
+}
+template <class C>
+BBT_DEV void row2_load_rest(cf* smem, const char* src, Mbar* bar) {
+  using R = Row2Cfg<C>;
+  constexpr unsigned kPiece = R::M * sizeof(cf);
+  constexpr unsigned kPitch = R::P * sizeof(cf);
+  char* dst = reinterpret_cast<char*>(smem);
+  mbar_expect_tx(bar, (32 - R::kSide) * kPiece);
+  for (unsigned i = R::kSide; i < 32; ++i)
+    bulk_load(dst + (size_t)i * kPitch, src + (size_t)i * kPiece, kPiece, bar,
+              i == 31);
+}
+
+template <class C, int LANDP>
 BBT_DEV void row2_load(cf* smem, const char* src, unsigned bytes, Mbar* bar) {
   char* dst = reinterpret_cast<char*>(smem);
-  if constexpr (LANDP) {
+  if constexpr (LANDP != 0) {
     constexpr unsigned kPiece = Row2Cfg<C>::M * sizeof(cf);
     constexpr unsigned kPitch = Row2Cfg<C>::P * sizeof(cf);
     const unsigned n = bytes / kPiece;
@@ -773,7 +808,7 @@ BBT_DEV void row2_load(cf* smem, const char* src, unsigned bytes, Mbar* bar) {
   }
 }
 
-template <class C, bool REGEN, bool LANDP>
+template <class C, bool REGEN, int LANDP>
 BBT_DEV_NOINLINE void dd_row2_tile(
     cf* smem, Mbar* bar, cf* row, const cf* chirp, const cf* tw,
     const cf* tw_sub, bool valid, unsigned phase, const char* next_src,
@@ -794,16 +829,28 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   cf* X = smem + (size_t)g * 32 * P;         // this row's [32][P] matrix
   const cf* tab_outer = reinterpret_cast<const cf*>(bar + 2);
   const cf* tab_sub = tab_outer + R::kTabOuter;
-  mbar_wait(bar, phase & 1u, phase);
   cf v[32];
-  stagger_in(grp, flags);
-  {
+  if constexpr (LANDP == 2) {
+    static_assert(LANDP != 2 || C::G == 1, "side buffer: one row per tile");
+    const cf* side = reinterpret_cast<const cf*>(
+        reinterpret_cast<const char*>(smem) + R::kSideOffset) + u;
+    mbar_wait(bar + 1, phase & 1u, phase);
+    stagger_in(grp, flags);
+#pragma unroll
+    for (int e = 0; e < R::kSide; ++e) v[e] = side[M * e];
+    mbar_wait(bar, phase & 1u, phase);
+#pragma unroll
+    for (int e = R::kSide; e < 32; ++e) v[e] = X[u + P * e];
+    stagger_out(grp, kGroups, flags);
+  } else {
+    mbar_wait(bar, phase & 1u, phase);
+    stagger_in(grp, flags);
     const cf* land = LANDP ? X + u : smem + g * C::N + u;
     constexpr int pitch = LANDP ? P : M;
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = valid ? land[pitch * e] : mk(0.f, 0.f);
+    stagger_out(grp, kGroups, flags);
   }
-  stagger_out(grp, kGroups, flags);
   // The landing zone becomes the exchange buffer once every thread has taken
   // its values (with LANDP a thread overwrites only what it took itself); the
   // butterflies in between need registers only.
@@ -815,6 +862,14 @@ BBT_DEV_NOINLINE void dd_row2_tile(
 #pragma unroll
   for (int r = 0; r < 32; ++r) X[r * P + u] = v[r];
   BBT_SYNC();
+  if constexpr (LANDP == 2) {
+    // Every thread has taken this row out of the side buffer: the next
+    // row's first pieces may land there.
+    if (tid == C::THREADS - 32 && next_bytes) {
+      fence_proxy_async();
+      row2_load_side<C>(smem, next_src, bar + 1);
+    }
+  }
   // From here to the next barrier warps do not wait for one another.
   cf* mine = X + k1 * P;
   stagger_in(grp, flags);
@@ -874,8 +929,12 @@ BBT_DEV_NOINLINE void dd_row2_tile(
 #endif
   if (tid == ((flags & 4) ? C::THREADS - 32 : 0) && next_bytes) {
     fence_proxy_async();
-    mbar_expect_tx(bar, next_bytes);
-    row2_load<C, LANDP>(smem, next_src, next_bytes, bar);
+    if constexpr (LANDP == 2) {
+      row2_load_rest<C>(smem, next_src, bar);
+    } else {
+      mbar_expect_tx(bar, next_bytes);
+      row2_load<C, LANDP>(smem, next_src, next_bytes, bar);
+    }
   }
   Dft<32>::run(v);
   if (valid) {
@@ -884,8 +943,9 @@ BBT_DEV_NOINLINE void dd_row2_tile(
   }
 }
 
-template <class C, bool REGEN, bool LANDP = false>
-BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
+template <class C, bool REGEN, int LANDP = 0>
+BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
+    dd_row2_kernel(DdArgs a) {
   cf* smem = BBT_SMEM(cf);
   Mbar* bar = reinterpret_cast<Mbar*>(smem + Row2Cfg<C>::kElems);
   {
@@ -921,14 +981,22 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, 1) dd_row2_kernel(DdArgs a) {
   // (A fixed tile-to-CTA map: rows are contiguous, so unlike the column
   // passes nothing is gained by handing the tiles out in order -- measured
   // 4 % slower, for the extra barrier.)
-  if (tid == 0) mbar_init(bar, 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+  }
   BBT_SYNC();
   if (tid == 0 && blockIdx.x < n_tiles) {
     unsigned rho0;
     const char* src = reinterpret_cast<const char*>(tile_base(blockIdx.x, rho0));
     const unsigned bytes = tile_bytes(rho0);
-    mbar_expect_tx(bar, bytes);
-    row2_load<C, LANDP>(smem, src, bytes, bar);
+    if constexpr (LANDP == 2) {
+      row2_load_side<C>(smem, src, bar + 1);
+      row2_load_rest<C>(smem, src, bar);
+    } else {
+      mbar_expect_tx(bar, bytes);
+      row2_load<C, LANDP>(smem, src, bytes, bar);
+    }
   }
   unsigned k = 0;
 #pragma unroll 1

@@ -297,7 +297,10 @@ INTER, PLANAR, HALF, FULLROW = 512, 256, 4096 | 8192, 16384   # plan hints
     (22, 2, 10), (24, 2, 0), (21, 3, 0),
     # planar rows of 2^11 .. 2^14 points (warp-local sub-transforms)
     (13, 2, 2 | PLANAR), (14, 1, 2 | PLANAR), (15, 1, 2 | PLANAR),
-    (15, 1, 1 | PLANAR), (16, 3, 2 | PLANAR)])
+    (15, 1, 1 | PLANAR), (16, 3, 2 | PLANAR),
+    # the same in 256-thread CTAs, two per SM (rows of up to 8192 points)
+    (16, 1, 3 | PLANAR | 8192), (16, 2, 3 | PLANAR | 8192),
+    (15, 2, 3 | PLANAR | 8192), (24, 2, 11 | PLANAR | 8192)])
 def test_dedisperse_large(backend, log2n, S, log2n1):
     if log2n > 16 and not backend.big:
         pytest.skip('too slow on host threads')
@@ -327,6 +330,37 @@ def test_dedisperse_large(backend, log2n, S, log2n1):
         assert_voltage(got, want)
     finally:
         dd.close()
+
+
+@pytest.mark.parametrize('log2n,log2n1,landp', [
+    (15, 2, 1), (15, 1, 1), (16, 2, 1), (15, 1, 2), (16, 2, 2), (15, 2, 2)])
+def test_dedisperse_row_landing_pitch(backend, log2n, log2n1, landp):
+    """Tuning knob row_landp: the row pass with its tiles landing at the pitch
+    of the exchange matrix (1: no barrier between the landing zone's reads and
+    the first exchange; 2, rows of 16384 points: half of the next row lands in
+    a side buffer a row ahead) computes what the default does."""
+    lib = backend.lib
+    rng = np.random.default_rng(900 + log2n + log2n1)
+    N = 1 << log2n
+    rate, f0, k = 16., 800., 1. / 2.41e-4
+    width = (1. / (f0 - rate / 2) ** 2 - 1. / (f0 + rate / 2) ** 2) * k
+    dm = (N / 5) / (rate * 1e6) / width
+    n_in = 2 * N + N // 3
+    n_in = 3 * N
+    probe = orc.DispersePlan(dm, f0, 1, rate, True, n_in, 1, (),
+                             fast_len=orc.next_pow2, samples_per_frame=1)
+    spf = N - probe.pad_start - probe.pad_end
+    lib.check(lib.bbt_tune_set(b'row_landp', landp))
+    try:
+        dd = Dd(backend, n_in, (), rate, f0, 1, dm, samples_per_frame=spf,
+                log2n1=log2n1 | PLANAR)
+        try:
+            x = cnoise(rng, (n_in,))
+            assert_voltage(dd.run(x), orc.disperse(x, dd.op))
+        finally:
+            dd.close()
+    finally:
+        lib.check(lib.bbt_tune_set(b'row_landp', 0))
 
 
 def test_dedisperse_set_response(backend):
