@@ -421,11 +421,27 @@ int bbt_pair_frames_exec(const void* in, void* out, int64_t n_in,
     return fail(BBT_EINVAL, "bad frame shape");
   if (n_frames <= 0) return BBT_OK;
   const int64_t n_pairs = (n_frames + 1) / 2;
-  BBT_LAUNCH(pair_frames_kernel, dim3(grid_for(n_pairs * n * n_series, 256)),
-             dim3(256), 0, as_stream(stream), static_cast<const float*>(in),
-             static_cast<cf*>(out), (long long)n_in,
-             (long long)samples_per_frame, (long long)n, (long long)n_series,
-             (long long)n_frames);
+  const int64_t per = n * n_series;
+  // Two values per thread where both frames of a pair stay 8-byte aligned.
+  const bool vec = !((samples_per_frame * n_series) & 1) && !(per & 1) &&
+                   !(reinterpret_cast<uintptr_t>(in) & 7) &&
+                   !(reinterpret_cast<uintptr_t>(out) & 15);
+  const unsigned gy = (unsigned)std::min<int64_t>(n_pairs, 65535);
+  const unsigned gx = (unsigned)std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div(per, 256 * (vec ? 2 : 1)),
+                           ceil_div((int64_t)sm_count() * 16, gy)));
+  if (vec)
+    BBT_LAUNCH(pair_frames_kernel<true>, dim3(gx, gy), dim3(256), 0,
+               as_stream(stream), static_cast<const float*>(in),
+               static_cast<cf*>(out), (long long)n_in,
+               (long long)samples_per_frame, (long long)n,
+               (long long)n_series, (long long)n_frames);
+  else
+    BBT_LAUNCH(pair_frames_kernel<false>, dim3(gx, gy), dim3(256), 0,
+               as_stream(stream), static_cast<const float*>(in),
+               static_cast<cf*>(out), (long long)n_in,
+               (long long)samples_per_frame, (long long)n,
+               (long long)n_series, (long long)n_frames);
   return check_launch("frame pairing kernel");
 }
 
@@ -437,11 +453,23 @@ int bbt_unpair_frames_exec(const void* in, void* out,
     return fail(BBT_EINVAL, "bad frame shape");
   if (n_frames <= 0) return BBT_OK;
   const int64_t n_pairs = (n_frames + 1) / 2;
-  BBT_LAUNCH(unpair_frames_kernel,
-             dim3(grid_for(n_pairs * samples_per_frame * n_series, 256)),
-             dim3(256), 0, as_stream(stream), static_cast<const cf*>(in),
-             static_cast<float*>(out), (long long)samples_per_frame,
-             (long long)n_series, (long long)n_frames);
+  const int64_t per = samples_per_frame * n_series;
+  const bool vec = !(per & 1) && !(reinterpret_cast<uintptr_t>(in) & 15) &&
+                   !(reinterpret_cast<uintptr_t>(out) & 7);
+  const unsigned gy = (unsigned)std::min<int64_t>(n_pairs, 65535);
+  const unsigned gx = (unsigned)std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div(per, 256 * (vec ? 2 : 1)),
+                           ceil_div((int64_t)sm_count() * 16, gy)));
+  if (vec)
+    BBT_LAUNCH(unpair_frames_kernel<true>, dim3(gx, gy), dim3(256), 0,
+               as_stream(stream), static_cast<const cf*>(in),
+               static_cast<float*>(out), (long long)samples_per_frame,
+               (long long)n_series, (long long)n_frames);
+  else
+    BBT_LAUNCH(unpair_frames_kernel<false>, dim3(gx, gy), dim3(256), 0,
+               as_stream(stream), static_cast<const cf*>(in),
+               static_cast<float*>(out), (long long)samples_per_frame,
+               (long long)n_series, (long long)n_frames);
   return check_launch("frame unpairing kernel");
 }
 

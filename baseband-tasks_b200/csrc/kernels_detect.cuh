@@ -1180,31 +1180,73 @@ BBT_GLOBAL void complex_to_real_kernel(const cf* BBT_RESTRICT in,
 //           (zero where the stream of n_in samples has ended)
 //   unpack: y[(2p) spf + m][s] = Re w[p][m][s], y[(2p+1) spf + m][s] = Im,
 //           m < spf, for the n_frames frames that exist.
+// (grid.y walks over the pairs, grid.x over the frame: no division per
+// element.  VEC: spf * S and N * S even, so that two neighbouring values of
+// either frame are one aligned 8-byte load and their pair one 16-byte store.)
+template <bool VEC>
 BBT_GLOBAL void pair_frames_kernel(const float* BBT_RESTRICT in,
                                    cf* BBT_RESTRICT out, long long n_in,
                                    long long spf, long long N, long long S,
                                    long long n_frames) {
-  const long long per = N * S, total = ((n_frames + 1) / 2) * per;
-  const long long limit = n_in * S;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-       i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / per, r = i - p * per;
-    const long long a = (2 * p) * spf * S + r, b = a + spf * S;
-    out[i] = mk(a < limit ? in[a] : 0.f,
-                2 * p + 1 < n_frames && b < limit ? in[b] : 0.f);
+  const long long per = N * S, limit = n_in * S;
+  const long long n_pairs = (n_frames + 1) / 2;
+  constexpr int W = VEC ? 2 : 1;
+  for (long long p = blockIdx.y; p < n_pairs; p += gridDim.y) {
+    const long long a0 = 2 * p * spf * S;
+    const bool second = 2 * p + 1 < n_frames;
+    const long long b0 = a0 + spf * S;
+    cf* o = out + p * per;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * W;
+         r < per; r += (long long)gridDim.x * blockDim.x * W) {
+      if constexpr (VEC) {
+        const long long a = a0 + r, b = b0 + r;
+        cf xa = mk(0.f, 0.f), xb = mk(0.f, 0.f);
+        if (a + 1 < limit) {
+          xa = *reinterpret_cast<const cf*>(in + a);
+        } else if (a < limit) {
+          xa.x = in[a];
+        }
+        if (second) {
+          if (b + 1 < limit) {
+            xb = *reinterpret_cast<const cf*>(in + b);
+          } else if (b < limit) {
+            xb.x = in[b];
+          }
+        }
+        cf2 z;
+        z.a = mk(xa.x, xb.x);
+        z.b = mk(xa.y, xb.y);
+        *reinterpret_cast<cf2*>(o + r) = z;
+      } else {
+        const long long a = a0 + r, b = b0 + r;
+        o[r] = mk(a < limit ? in[a] : 0.f, second && b < limit ? in[b] : 0.f);
+      }
+    }
   }
 }
+template <bool VEC>
 BBT_GLOBAL void unpair_frames_kernel(const cf* BBT_RESTRICT in,
                                      float* BBT_RESTRICT out, long long spf,
                                      long long S, long long n_frames) {
   const long long per = spf * S, n_pairs = (n_frames + 1) / 2;
-  const long long total = n_pairs * per;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-       i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / per, r = i - p * per;
-    const cf w = in[i];
-    out[(2 * p) * per + r] = w.x;
-    if (2 * p + 1 < n_frames) out[(2 * p + 1) * per + r] = w.y;
+  constexpr int W = VEC ? 2 : 1;
+  for (long long p = blockIdx.y; p < n_pairs; p += gridDim.y) {
+    const cf* w = in + p * per;
+    float* re = out + (2 * p) * per;
+    float* im = re + per;
+    const bool second = 2 * p + 1 < n_frames;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * W;
+         r < per; r += (long long)gridDim.x * blockDim.x * W) {
+      if constexpr (VEC) {
+        const cf2 z = *reinterpret_cast<const cf2*>(w + r);
+        *reinterpret_cast<cf*>(re + r) = mk(z.a.x, z.b.x);
+        if (second) *reinterpret_cast<cf*>(im + r) = mk(z.a.y, z.b.y);
+      } else {
+        const cf z = w[r];
+        re[r] = z.x;
+        if (second) im[r] = z.y;
+      }
+    }
   }
 }
 

@@ -382,8 +382,9 @@ def test_dedisperse_set_response(backend):
         dd.close()
 
 
-@pytest.mark.parametrize('n_frames,S', [(1, 1), (4, 2), (5, 3)])
-def test_real_frames_in_pairs(backend, n_frames, S):
+@pytest.mark.parametrize('n_frames,S,cut', [
+    (1, 1, 300), (4, 2, 300), (5, 3, 300), (3, 1, 301), (4, 3, 301)])
+def test_real_frames_in_pairs(backend, n_frames, S, cut):
     """A real-valued stream through the complex plan two frames at a time
     (bbt_pair_frames_exec / bbt_unpair_frames_exec): with a real response --
     the Hermitian extension of the rfft phase factor -- the real and imaginary
@@ -393,7 +394,8 @@ def test_real_frames_in_pairs(backend, n_frames, S):
     empty."""
     b, lib = backend, backend.lib
     rng = np.random.default_rng(100 * n_frames + S)
-    N, pad_start, spf = 2048, 100, 2048 - 300
+    # (An odd number of values per frame takes the kernels' scalar path.)
+    N, pad_start, spf = 2048, 100, 2048 - cut
     n_in = (n_frames - 1) * spf + N
     x = rng.standard_normal((n_in, S)).astype('f4')
     half = np.exp(2j * np.pi * rng.uniform(size=(1, N // 2 + 1)))
