@@ -229,6 +229,23 @@ int launch_dd_row(const DdArgs& a0, int64_t n_frames, bbt_stream_t st) {
   }
   if constexpr (PLANAR && !HALF) {
     // Persistent CTAs fed by bulk copies (one tile = one contiguous range).
+    if constexpr (L2 == 14) {
+      // Sixteen values per thread in 1024-thread CTAs: 8 warps per scheduler
+      // instead of 4, at 64 registers and one more exchange per transform
+      // (A/B knob row_e16; rows in natural order, i.e. plans made with row2=0).
+      if (tune("row_e16", 0) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
+        using C16 = FftCfg<L2, 4, 1024>;
+        const size_t smem = C16::SMEM_BYTES + sizeof(Mbar);
+        auto kern = dd_row_tma_kernel<C16>;
+        if (BBT_SET_SMEM(kern, smem))
+          return fail(BBT_ECUDA, "cannot set shared memory size");
+        const int64_t ctas =
+            std::min<int64_t>(n1 * a.S * n_frames, (int64_t)sm_count());
+        prof_next_name = "dd_row";
+        BBT_LAUNCH(kern, dim3((unsigned)ctas), dim3(C16::THREADS), smem, st, a);
+        return check_launch("dedispersion row kernel");
+      }
+    }
     if (tune("row_tma", 1) && !(reinterpret_cast<uintptr_t>(a.work) & 15)) {
       const size_t smem = C::SMEM_BYTES + sizeof(Mbar);
       auto kern = dd_row_tma_kernel<C>;

@@ -332,25 +332,31 @@ def test_dedisperse_large(backend, log2n, S, log2n1):
         dd.close()
 
 
-@pytest.mark.parametrize('log2n,log2n1,landp', [
-    (15, 2, 1), (15, 1, 1), (16, 2, 1), (15, 1, 2), (16, 2, 2), (15, 2, 2)])
-def test_dedisperse_row_landing_pitch(backend, log2n, log2n1, landp):
-    """Tuning knob row_landp: the row pass with its tiles landing at the pitch
-    of the exchange matrix (1: no barrier between the landing zone's reads and
-    the first exchange; 2, rows of 16384 points: half of the next row lands in
-    a side buffer a row ahead) computes what the default does."""
+@pytest.mark.parametrize('log2n,log2n1,knobs', [
+    (15, 2, dict(row_landp=1)), (15, 1, dict(row_landp=1)),
+    (16, 2, dict(row_landp=1)), (15, 1, dict(row_landp=2)),
+    (16, 2, dict(row_landp=2)), (15, 2, dict(row_landp=2)),
+    (15, 1, dict(row2=0, row_e16=1)), (16, 2, dict(row2=0, row_e16=1))])
+def test_dedisperse_row_variants(backend, log2n, log2n1, knobs):
+    """Tuning knobs of the row pass compute what the default does.
+    row_landp: tiles land at the pitch of the exchange matrix (1: no barrier
+    between the landing zone's reads and the first exchange; 2, rows of 16384
+    points: half of the next row lands in a side buffer a row ahead).
+    row_e16 (with row2=0): rows of 16384 points with 16 values per thread in
+    1024-thread CTAs."""
     lib = backend.lib
     rng = np.random.default_rng(900 + log2n + log2n1)
     N = 1 << log2n
     rate, f0, k = 16., 800., 1. / 2.41e-4
     width = (1. / (f0 - rate / 2) ** 2 - 1. / (f0 + rate / 2) ** 2) * k
     dm = (N / 5) / (rate * 1e6) / width
-    n_in = 2 * N + N // 3
     n_in = 3 * N
     probe = orc.DispersePlan(dm, f0, 1, rate, True, n_in, 1, (),
                              fast_len=orc.next_pow2, samples_per_frame=1)
     spf = N - probe.pad_start - probe.pad_end
-    lib.check(lib.bbt_tune_set(b'row_landp', landp))
+    defaults = dict(row_landp=0, row2=1, row_e16=0)
+    for key, value in knobs.items():
+        lib.check(lib.bbt_tune_set(key.encode(), value))
     try:
         dd = Dd(backend, n_in, (), rate, f0, 1, dm, samples_per_frame=spf,
                 log2n1=log2n1 | PLANAR)
@@ -360,7 +366,8 @@ def test_dedisperse_row_landing_pitch(backend, log2n, log2n1, landp):
         finally:
             dd.close()
     finally:
-        lib.check(lib.bbt_tune_set(b'row_landp', 0))
+        for key in knobs:
+            lib.check(lib.bbt_tune_set(key.encode(), defaults[key]))
 
 
 def test_dedisperse_set_response(backend):
