@@ -112,8 +112,11 @@ def test_reference_framing(bt, reference_frequency):
     on that framing."""
     import bbt_oracle as orc
     from test_kernels import assert_voltage
+    from baseband_tasks_b200 import _cabi
     from baseband_tasks_b200.fourier import fft_maker
     from baseband_tasks_b200.fourier.cuda import smooth_fast_len
+    if _cabi._DEVICE.type == 'cpu' and reference_frequency is not None:
+        pytest.skip('one framing is enough on host threads (a minute each)')
     for n in (1, 7, 8, 130, 4095, 19324 + 6400, 24000, 100003):
         assert smooth_fast_len(n) == orc.next_fast_len(n)
     assert smooth_fast_len(130) == 135          # tests/test_base.py:522-537

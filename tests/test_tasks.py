@@ -253,7 +253,10 @@ def make_chain(bt, x, rate, freq, dm, n_chan, spf, device_input):
 @pytest.mark.parametrize('device_input', [False, True])
 def test_chain_dedisperse_channelize_power_integrate(bt, device_input):
     rng = np.random.default_rng(11)
-    n, rate, dm, n_chan = 20000, 1e6, 3., 64
+    from baseband_tasks_b200 import _cabi
+    # (Four frames; three where the kernels run on host threads.)
+    n = 12000 if _cabi._DEVICE.type == 'cpu' else 20000
+    rate, dm, n_chan = 1e6, 3., 64
     freq = np.array([[300e6], [301e6], [302e6]])
     x = cnoise(rng, (n, 3, 2))
     src, dd, ch, pw = make_chain(bt, x, rate, freq, dm, n_chan, 4096 - 600,
@@ -962,24 +965,31 @@ def test_power_fused_into_dedispersion(bt, shape):
     rate, dm = 1e6, 2.
     n_chan = int(np.prod(shape[:-1], dtype=int))
     freq = (300e6 + 1e6 * np.arange(n_chan)).reshape(shape[:-1] + (1,))
-    n = 3 * 32768 + 5000
+    # (Host-thread emulation: the many-series cases on shorter frames, which
+    # go through the same three passes.)
+    from baseband_tasks_b200 import _cabi
+    emulated = _cabi._DEVICE.type == 'cpu'
+    nf = 8192 if emulated and n_chan > 1 else 32768
+    spf = nf - 1000
+    n = 3 * nf + 5000
     x = cnoise(np.random.default_rng(5), (n,) + shape)
     kw = dict(frequency=freq if n_chan > 1 else 300e6, sideband=1,
               polarization=np.array(['X', 'Y']))
     src = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=4096, **kw)
-    dd = bt.Dedisperse(src, dm, samples_per_frame=32768 - 1000)
+    dd = bt.Dedisperse(src, dm, samples_per_frame=spf)
+    nf = dd._ih_samples_per_frame    # (more with the delay between channels)
     fused = bt.Power(dd)
     assert fused._fused
     src2 = bt.ArrayStream(x, start_time(bt), rate, samples_per_frame=4096, **kw)
-    dd2 = bt.Dedisperse(src2, dm, samples_per_frame=32768 - 1000)
+    dd2 = bt.Dedisperse(src2, dm, samples_per_frame=spf)
     v = dd2.read()
     want = orc.power(v.astype(np.complex128), axis=v.ndim - 1)
     assert fused.shape == want.shape
     got = fused.read()
     assert got.dtype == np.float32
     assert_power(got, want)
-    fused.seek(31000)
-    assert_power(fused.read(2000), want[31000:33000])
+    fused.seek(spf - 768)       # across a frame boundary
+    assert_power(fused.read(2000), want[spf - 768:spf + 1232])
     # The voltages are still what they were.
     dd.seek(100)
     assert_voltage(dd.read(50), v[100:150])
@@ -987,7 +997,8 @@ def test_power_fused_into_dedispersion(bt, shape):
     # slices of the result).
     from baseband_tasks_b200 import base
     saved = base.BLOCK_BYTES
-    base.BLOCK_BYTES = 40000 * 16 * (fused.shape[1] if fused.ndim > 2 else 1)
+    base.BLOCK_BYTES = (nf + nf // 4) * 16 * (fused.shape[1]
+                                              if fused.ndim > 2 else 1)
     try:
         fused.seek(0)
         assert_power(fused.read(), want)
