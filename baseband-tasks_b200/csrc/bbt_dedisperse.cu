@@ -9,6 +9,7 @@ struct bbt_dedisperse_plan {
   int64_t n, n_series, pad_start, n_valid, n_chirp;
   int log2n, log2n1, log2n2;
   int planar;      // work-buffer layout of the three-pass split
+  int64_t work_pitch;  // series pitch of the work buffer (>= n_series)
   int half;        // 256-thread CTAs, half-size tiles
   int row2;        // row pass by dd_row2_kernel (chirp rows in its order)
   const cf* tw_sub;  // roots of unity for its sub-transforms (n2 / 32)
@@ -71,7 +72,8 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
     strides[0] = 8, strides[1] = N2 * 8, strides[2] = S * N2 * 8;
     box[0] = m.tn, box[1] = (uint32_t)S, box[2] = m.box_rows;
   } else {
-    const int64_t frame_stride = inverse ? a.N * a.S : a.in_frame_stride;
+    const int64_t frame_stride = inverse ? a.N * a.Sw : a.in_frame_stride;
+    if (a.Sw != a.S) return BBT_EUNSUPPORTED;  // padded rows: per-thread loads
     if (frame_stride & 1) return BBT_EUNSUPPORTED;
     base = inverse ? static_cast<void*>(a.work)
                    : const_cast<void*>(static_cast<const void*>(a.in));
@@ -91,7 +93,7 @@ int launch_dd_col_tma(bool inverse, const DdArgs& a, int64_t n_frames,
   // Tile counter of this pass, behind the frames in the work buffer.
   m.next_tile = reinterpret_cast<unsigned*>(
                     reinterpret_cast<char*>(a.work) +
-                    n_frames * a.N * a.S * (int64_t)sizeof(cf)) +
+                    n_frames * a.N * a.Sw * (int64_t)sizeof(cf)) +
                 (inverse ? 16 : 0);
   if (dev_zero(m.next_tile, sizeof(unsigned), st))
     return fail(BBT_ECUDA, "cannot reset the tile counter");
@@ -377,6 +379,15 @@ int bbt_dedisperse_plan_create(bbt_dedisperse_plan** plan, int64_t n,
     if (!planar && !((hint >> 14) & 1) && !whole_rows) p->half |= 2;
   }
   // Long contiguous rows: the formulation with warp-local sub-transforms.
+  // Interleaved rows of many series whose count is not a multiple of eight
+  // (C3: 2050) would put the 64-byte runs of a tile at odd offsets, every one
+  // straddling sectors in all three passes: the work buffer pads the series
+  // to a multiple of eight.  (Only where the column passes are the
+  // per-thread-load kernels, N1 <= 16: the tensor-map tiles walk flat columns.)
+  p->work_pitch = n_series;
+  if (p->log2n1 > 0 && !p->planar && n_series > 16 && (n_series & 7) &&
+      p->log2n1 <= 4 && tune("dd_work_pad", 1))
+    p->work_pitch = (n_series + 7) & ~int64_t(7);
   p->row2 = p->log2n1 > 0 && p->planar && p->log2n2 >= 11 &&
             (!(p->half & 2) || p->log2n2 <= 13) && tune("row2", 1);
   p->tw_sub = p->row2 ? twiddle_table(p->log2n2 - 5) : nullptr;
@@ -508,7 +519,7 @@ int64_t bbt_dedisperse_work_bytes(const bbt_dedisperse_plan* p,
   // Frames x points, and behind them the tile counters of the persistent
   // column passes (one per pass).
   return std::min<int64_t>(n_frames, kMaxFramesPerLaunch) * p->n *
-             p->n_series * (int64_t)sizeof(cf) + kCounterBytes;
+             p->work_pitch * (int64_t)sizeof(cf) + kCounterBytes;
 }
 
 }  // extern "C"
@@ -595,6 +606,7 @@ static int dedisperse_exec_run(const bbt_dedisperse_plan* p, const void* in,
   a.out_frame_stride = out_frame_stride;
   a.N = p->n;
   a.S = p->n_series;
+  a.Sw = p->work_pitch;
   a.log2n1 = p->log2n1;
   a.log2n2 = p->log2n2;
   a.planar = p->planar;

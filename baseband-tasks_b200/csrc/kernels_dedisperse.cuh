@@ -43,6 +43,9 @@ struct DdArgs {
   const int* series_map;  // series -> chirp index
   long long in_frame_stride, out_frame_stride;  // in complex elements
   long long N, S;       // frame length, interleaved series
+  long long Sw;         // series pitch of the work buffer: S, or (interleaved
+                        // layout, many series) S rounded up so that every
+                        // run of a tile starts on a 64-byte boundary
   int log2n1, log2n2;
   int planar;           // work-buffer layout
   long long lo, hi;     // valid flat range [(pad_start+skip)*S, (pad_start+spf)*S)
@@ -151,16 +154,16 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   if (valid) {
     const unsigned n2 = (unsigned)col / (unsigned)a.S;
     col_twiddle<C, 0>(v, a.big, (int)n2, t, 1.f);
-    cf* dst = a.work + frame * a.N * a.S;
+    cf* dst = a.work + frame * a.N * a.Sw;
     long long step;
+    const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
+    const long long N2 = a.N >> a.log2n1;
     if (a.planar) {
-      const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
-      const long long N2 = a.N >> a.log2n1;
       dst += s * N2 + n2;
       step = a.S * N2;
     } else {
-      dst += col;
-      step = n2s;
+      dst += (long long)n2 * a.Sw + s;
+      step = N2 * a.Sw;
     }
     dst += (long long)t * step;
     const long long pstep = (long long)C::T * step;
@@ -203,17 +206,19 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   const long long col = (long long)blockIdx.x * C::G + g;
   const long long frame = blockIdx.y;
   const bool valid = col < n2s;
-  const cf* src = a.work + frame * a.N * a.S;
+  const cf* src = a.work + frame * a.N * a.Sw;
   long long step;
-  if (a.planar) {
+  {
     const unsigned n2 = (unsigned)col / (unsigned)a.S;
     const unsigned s = (unsigned)col - n2 * (unsigned)a.S;
     const long long N2 = a.N >> a.log2n1;
-    src += s * N2 + n2;
-    step = a.S * N2;
-  } else {
-    src += col;
-    step = n2s;
+    if (a.planar) {
+      src += s * N2 + n2;
+      step = a.S * N2;
+    } else {
+      src += (long long)n2 * a.Sw + s;
+      step = N2 * a.Sw;
+    }
   }
   cf v[C::E];
   {
@@ -233,7 +238,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     }
     if (nf < gridDim.y && nb < gridDim.x) {
       const long long c0 = nb * C::G;
-      const cf* base = a.work + nf * a.N * a.S;
+      const cf* base = a.work + nf * a.N * a.Sw;
       if (a.planar) {
         // Runs of the tile's n2 values, one per (k1, s).
         const long long N2 = a.N >> a.log2n1;
@@ -246,8 +251,11 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
                         C::THREADS);
       } else {
         const long long left = n2s - c0;
-        prefetch_tile(base + c0, C::N, n2s, left < C::G ? (int)left : C::G,
-                      tid, C::THREADS);
+        const unsigned n20 = (unsigned)c0 / (unsigned)a.S;
+        const unsigned s0 = (unsigned)c0 - n20 * (unsigned)a.S;
+        prefetch_tile(base + (long long)n20 * a.Sw + s0, C::N,
+                      (a.N >> a.log2n1) * a.Sw,
+                      left < C::G ? (int)left : C::G, tid, C::THREADS);
       }
     }
   }
@@ -301,7 +309,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
   int t, g;
   long long k1, s, stride;
   bool valid;
-  cf* row = a.work + frame * a.N * a.S;
+  cf* row = a.work + frame * a.N * a.Sw;
   if (PLANAR) {
     t = tid % C::T;
     g = tid / C::T;
@@ -321,8 +329,8 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     k1 = rblk * rpc + kl;
     s = chunk * sc + sl;
     valid = kl < rpc && k1 < n1 && s < a.S;
-    row += k1 * C::N * a.S + s;
-    stride = a.S;
+    row += k1 * C::N * a.Sw + s;
+    stride = a.Sw;
   }
   const cf* chirp = a.chirp;
   if (valid) chirp += ((long long)a.series_map[s] * n1 + k1) * C::N;
@@ -344,7 +352,7 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
     const unsigned nb = nlin / (unsigned)a.n_frames;
     const unsigned nf = nlin - nb * (unsigned)a.n_frames;
     if (nlin < gridDim.x) {
-      const cf* base2 = a.work + nf * a.N * a.S;
+      const cf* base2 = a.work + nf * a.N * a.Sw;
       long long elems = (long long)C::G * C::N;
       if (PLANAR) {
         base2 += (long long)nb * C::G * C::N;
@@ -361,17 +369,18 @@ BBT_GLOBAL void BBT_LAUNCH_BOUNDS(C::THREADS, (C::THREADS <= 256 ? 2 : 1))
           // fetched by one to still be in L2 when the others come for them
           // (measured: 2.6 x the data read from DRAM).  Each tile's own
           // runs, then: rpc * N of them, S elements apart.
-          prefetch_tile(base2 + ((long long)rb * a.row_rpc) * C::N * a.S +
+          prefetch_tile(base2 + ((long long)rb * a.row_rpc) * C::N * a.Sw +
                             (long long)ck * a.row_sc,
-                        (int)a.row_rpc * C::N, a.S, (int)a.row_sc, tid,
+                        (int)a.row_rpc * C::N, a.Sw, (int)a.row_sc, tid,
                         C::THREADS);
           elems = 0;
         } else {
-          elems = (long long)a.row_rpc * C::N * a.S / chunks;
-          base2 += ((long long)rb * a.row_rpc) * C::N * a.S + ck * elems;
+          elems = (long long)a.row_rpc * C::N * a.Sw / chunks;
+          base2 += ((long long)rb * a.row_rpc) * C::N * a.Sw + ck * elems;
         }
       }
-      const long long limit = a.N * a.S - (base2 - (a.work + nf * a.N * a.S));
+      const long long limit =
+          a.N * a.Sw - (base2 - (a.work + nf * a.N * a.Sw));
       if (elems > limit) elems = limit;
       for (long long i = (long long)tid * 16; i < elems;
            i += (long long)C::THREADS * 16)
