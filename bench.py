@@ -678,14 +678,28 @@ def run_c3(args, rank, world, local):
     chain2 = chain_on(stage)
     out_host = []
 
+    # The result (2.1 GB of powers per step) takes four times as long over
+    # PCIe as the 8-bit input: it is copied back on a stream of its own, into
+    # alternating pinned buffers, while the next step's input arrives and is
+    # processed; the timed region ends when the last copy has landed.
+    d2h_stream = torch.cuda.Stream()
+    n_e2e = [0]
+
     def step_e2e():
+        main = torch.cuda.current_stream()
         stage.copy_(host, non_blocking=True)
         chain2.seek(0)
         res = chain2.read_device()
-        if not out_host:
+        while len(out_host) < 2:
             out_host.append(torch.empty(res.shape, dtype=res.dtype,
                                         pin_memory=True))
-        out_host[0].copy_(res, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        d2h_stream.wait_event(ev)
+        with torch.cuda.stream(d2h_stream):
+            out_host[n_e2e[0] & 1].copy_(res, non_blocking=True)
+            res.record_stream(d2h_stream)
+        n_e2e[0] += 1
         return res
 
     def barrier():
@@ -704,6 +718,7 @@ def run_c3(args, rank, world, local):
         e0.record()
         for _ in range(steps):
             fn()
+        torch.cuda.current_stream().wait_stream(d2h_stream)
         e1.record()
         barrier()
         windows.append((t0, time.monotonic()))
