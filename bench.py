@@ -395,9 +395,14 @@ def run_b200(args):
     # pieces of whole frames on a copy stream; the chain works on the output
     # the pieces that have arrived determine (successive reads through the
     # public API), and every partial result is copied back.
-    dev_stage = torch.empty_like(dev_in)
-    chain_e2e = job.chain(dev_stage)
-    run_e2e = job.runner(chain_e2e)
+    # Two staging buffers, each with a chain of its own, take turns: the
+    # input of step k+1 arrives while step k is still being processed and
+    # its result copied back.
+    dev_stages = [torch.empty_like(dev_in) for _ in range(2)]
+    chains_e2e = [job.chain(d) for d in dev_stages]
+    runs_e2e = [job.runner(c) for c in chains_e2e]
+    stage_free = [None, None]     # recorded when a step is done with a buffer
+    n_e2e = [0]
     copy_stream = torch.cuda.Stream()
     d2h_stream = torch.cuda.Stream()
     n_pieces = 4 if not w.get('fold') else 1
@@ -418,14 +423,19 @@ def run_b200(args):
 
     def step_e2e(src_host=None, decode=None):
         main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)      # previous step is done with it
+        k = n_e2e[0] & 1
+        n_e2e[0] += 1
+        dev_stage, run_e2e = dev_stages[k], runs_e2e[k]
+        raw = decode[0][k] if decode is not None else None
+        if stage_free[k] is not None:      # the step before last is done with it
+            copy_stream.wait_event(stage_free[k])
         events = []
         with torch.cuda.stream(copy_stream):
             for a, b in pieces:
                 if decode is None:
                     dev_stage[a:b].copy_(host[a:b], non_blocking=True)
                 else:
-                    decode[0][a:b].copy_(src_host[a:b], non_blocking=True)
+                    raw[a:b].copy_(src_host[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append(ev)
@@ -434,7 +444,7 @@ def run_b200(args):
             main.wait_event(events[i])
             if decode is not None:
                 lib.check(lib.bbt_decode_exec(
-                    ctypes.c_void_p(decode[0][a:b].data_ptr()),
+                    ctypes.c_void_p(raw[a:b].data_ptr()),
                     ctypes.c_void_p(dev_stage[a:b].data_ptr()),
                     ctypes.c_void_p(decode[1].data_ptr()),
                     (b - a) * 2 * job.S, 8, ctypes.c_void_p(main.cuda_stream)))
@@ -453,7 +463,8 @@ def run_b200(args):
             with torch.cuda.stream(d2h_stream):
                 out_host[key].copy_(res, non_blocking=True)
                 res.record_stream(d2h_stream)
-        main.wait_stream(d2h_stream)
+        stage_free[k] = torch.cuda.Event()
+        stage_free[k].record(main)
         return res
 
     def barrier():
@@ -472,6 +483,8 @@ def run_b200(args):
         e0.record()
         for _ in range(steps):
             fn()
+        # (the last results' copies to the host are part of the region)
+        torch.cuda.current_stream().wait_stream(d2h_stream)
         e1.record()
         barrier()
         windows.append((t0, time.monotonic()))
@@ -502,7 +515,7 @@ def run_b200(args):
     levels8 = bt.payload_levels(8) / 30.
     host8 = torch.from_numpy(bt.encode_payload(
         host.numpy(), 8, levels8).reshape(n_block, -1)).pin_memory()
-    dev8 = torch.empty_like(host8, device='cuda')
+    dev8 = [torch.empty_like(host8, device='cuda') for _ in range(2)]
     d_levels8 = torch.from_numpy(levels8).cuda()
     for _ in range(2):
         step_e2e(host8, (dev8, d_levels8))
@@ -527,7 +540,7 @@ def run_b200(args):
     # Strong scaling: a fixed stream of 64 frames split over the ranks.
     strong = None
     if not w.get('only_dedisperse') and args.strong:
-        del dev_stage, chain_e2e, run_e2e
+        del dev_stages, chains_e2e, runs_e2e
         torch.cuda.empty_cache()
         sjob = Job(w, rank, world, frames=64)
         g = torch.Generator(device='cuda').manual_seed(w['seed'] + rank)
